@@ -1,0 +1,175 @@
+/* =====================================================================================
+ * lgar_b200.h -- C ABI of the B200-native LGAR time-stepping core (liblgar_b200.so).
+ *
+ * This library replaces, for MANY independent soil columns at once, the per-column
+ * update loop of the reference (paths relative to /root/reference/dpLGAR/):
+ *
+ *   lgar_forward   <->  models/dpLGAR.py:154-299  dpLGAR.forward(x) applied to every row of the
+ *                       forcing record (the loop of agents/DifferentiableLGAR.py:117-125 with
+ *                       MassBalance.change_mass resetting the accumulators after each step),
+ *                       starting from models/dpLGAR.py:97-147 set_internal_states().
+ *   lgar_backward  <->  loss.backward() of agents/DifferentiableLGAR.py:163 restricted to the
+ *                       model parameters alpha/n/ksat (models/dpLGAR.py:50-57): reverse-mode
+ *                       through the same step loop (reference autograd semantics).
+ *   status[B]      <->  the Python exceptions the reference uses as error reporting
+ *                       (physics/utils.py:17-27,181-183; physics/layers/Layer.py:1206-1208,
+ *                       :980 (Q9), :876-881 (Q10), :1115).
+ *
+ * The reference has no FFI layer (it is pure Python); the binding a maintainer adds is the
+ * ctypes stub shown in INTEGRATION.md (== lgar-py_b200/_capi.py).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch types.  Every function returns 0 on success or a
+ *     negative LGAR_E_* code; lgar_last_error_string() describes the last failure of the
+ *     calling thread.  Nothing throws across the ABI.
+ *   - `*_dev` pointers are device pointers on the current CUDA device; the caller owns all
+ *     buffers.  `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are
+ *     asynchronous with respect to the host unless stated otherwise.
+ *   - re-entrant per (stream, workspace): no global mutable state besides the per-thread
+ *     error string and a lazily cached device-attribute query.
+ *   - all floating point data is IEEE fp64; layouts have the COLUMN index fastest so that a
+ *     warp of 32 columns reads/writes 256 contiguous bytes.
+ * ===================================================================================== */
+#ifndef LGAR_B200_H
+#define LGAR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGAR_ABI_VERSION 1
+#define LGAR_MAX_LAYERS 4      /* soil layers per column (all reference configs use 3)            */
+#define LGAR_MAX_FRONTS 16     /* capacity of the wetting-front list of one column                */
+#define LGAR_MAX_GIUH 8        /* GIUH ordinates (reference: 5, data/config/Phillipsburg.yaml)    */
+#define LGAR_NUM_OUTPUTS 10
+
+/* per-forcing-step output variables (index into the [NOUT][T][B] output array); the same
+ * accumulators MassBalance.change_mass reads and zeroes (physics/MassBalance.py:31-53)          */
+enum lgar_output {
+  LGAR_OUT_RUNOFF = 0,
+  LGAR_OUT_PERCOLATION = 1,
+  LGAR_OUT_AET = 2,
+  LGAR_OUT_INFILTRATION = 3,
+  LGAR_OUT_ENDING_VOLUME = 4,   /* state at the end of the step (not an accumulator)              */
+  LGAR_OUT_PONDED_WATER = 5,    /* state at the end of the step                                   */
+  LGAR_OUT_GIUH_RUNOFF = 6,
+  LGAR_OUT_PRECIP = 7,
+  LGAR_OUT_PET = 8,
+  LGAR_OUT_DISCHARGE = 9
+};
+
+/* per-column status: 0 = OK; otherwise the reference would have raised at `crash_step`.       */
+enum lgar_status {
+  LGAR_ST_OK = 0,
+  LGAR_ST_NEG_POW = 1,        /* ValueError, negative base in safe_pow      utils.py:25-27        */
+  LGAR_ST_NAN = 2,            /* ValueError, NaN in pow input/result        utils.py:17-19,181-183 */
+  LGAR_ST_THETA_ORDER = 3,    /* ValueError, theta_1 > theta_2 in layer 0   Layer.py:1206-1208    */
+  LGAR_ST_BOTTOM_REACHED = 4, /* AttributeError, front left the last layer  Layer.py:980 (Q9)     */
+  LGAR_ST_NULL_NEIGHBOUR = 5, /* AttributeError/UnboundLocalError           Layer.py:876-881 (Q10)*/
+  LGAR_ST_FRONT_OVERFLOW = 6, /* more than `max_fronts` fronts (capacity of this library)         */
+  LGAR_ST_ITER_CAP = 7,       /* a root finder exceeded `iter_cap` iterations                     */
+  LGAR_ST_INDEX_ERROR = 8     /* IndexError                                 Layer.py:1115         */
+};
+
+enum lgar_error {
+  LGAR_E_OK = 0,
+  LGAR_E_INVALID = -1,   /* bad argument                                                        */
+  LGAR_E_CUDA = -2,      /* CUDA runtime error (see lgar_last_error_string)                     */
+  LGAR_E_NO_DEVICE = -3, /* no sm_100 device: there is NO CPU fallback                          */
+  LGAR_E_WORKSPACE = -4  /* workspace too small                                                 */
+};
+
+/* Problem description.  Array members are device pointers (lgar_forward/backward) or host
+ * pointers (lgar_forward_host).  [L][B] means layer-major, column fastest.                    */
+typedef struct lgar_problem {
+  int32_t abi_version;     /* = LGAR_ABI_VERSION                                                */
+  int32_t num_columns;     /* B                                                                 */
+  int32_t num_layers;      /* L <= LGAR_MAX_LAYERS          cfg.data.layer_thickness            */
+  int32_t num_steps;       /* T forcing steps                cfg.models.nsteps                  */
+  int32_t num_subcycles;   /* S sub-steps per forcing step   cfg.models.num_subcycles           */
+  int32_t num_sites;       /* number of forcing series                                          */
+  int32_t nint;            /* Geff trapezoid intervals       cfg.constants.nint (120)           */
+  int32_t num_giuh;        /* <= LGAR_MAX_GIUH               cfg.data.giuh_ordinates            */
+  int32_t max_fronts;      /* 8, 12 or 16 (0 = 16): front-list capacity per column              */
+  int32_t chunk_steps;     /* forcing steps per scheduling/checkpoint chunk (0 = default 64)    */
+  int64_t iter_cap;        /* root-finder iteration cap (0 = default 1,000,000)                 */
+  double subcycle_length_h;   /* dt in hours                 cfg.models.subcycle_length_h       */
+  double wilting_point_psi;   /* cm                          cfg.data.wilting_point_psi         */
+  double frozen_factor;       /*                             cfg.constants.frozen_factor        */
+  double giuh_ordinates[LGAR_MAX_GIUH];
+  /* learnable parameters, models/dpLGAR.py:50-57 (ksat already multiplied by frozen_factor)   */
+  const double* alpha;        /* [L][B]  1/cm                                                    */
+  const double* n;            /* [L][B]                                                          */
+  const double* ksat;         /* [L][B]  cm/h                                                    */
+  /* static soil/site data                                                                      */
+  const double* theta_r;      /* [L][B]                      soils table column theta_r         */
+  const double* theta_e;      /* [L][B]                      soils table column theta_e         */
+  const double* thickness;    /* [L][B]  cm                  cfg.data.layer_thickness           */
+  const double* initial_psi;  /* [B]     cm                  cfg.data.initial_psi               */
+  const double* ponded_depth_max; /* [B] cm                  cfg.data.ponded_depth_max          */
+  /* forcing, data/Data.py:33-40: x[t] = (P, PET) in cm/h                                       */
+  const double* forcing;      /* [num_sites][T][2]                                               */
+  const int32_t* site_index;  /* [B] forcing series of each column (NULL = all use series 0)    */
+} lgar_problem;
+
+/* Output buffers.  Any pointer may be NULL (that output is skipped).                           */
+typedef struct lgar_outputs {
+  double* per_step;        /* [NOUT][T][B]; rows selected by per_step_mask are written, the
+                              others are left untouched                                          */
+  uint32_t per_step_mask;  /* bit k = write output k                                            */
+  int32_t reserved0;
+  double* sums;            /* [NOUT][B]: sum over t of every output (ENDING_VOLUME and
+                              PONDED_WATER: value after the last step)                          */
+  double* start_volume;    /* [B] water in the column after set_internal_states()               */
+  int32_t* status;         /* [B] lgar_status                                                   */
+  int32_t* crash_step;     /* [B] forcing step at which status became non-zero, else -1         */
+  int32_t* num_fronts;     /* [T][B] number of wetting fronts after every step                  */
+  /* full front-list dump after every step (parity tests; small B only)                        */
+  double* fronts;          /* [T][MAXF=16][5][B]: depth, theta, psi_cm, k_cm_per_h, dzdt        */
+  int8_t* front_layer;     /* [T][16][B] layer_num (-1 = no front)                              */
+  int8_t* front_to_bottom; /* [T][16][B]                                                        */
+  /* work counters, summed over columns and steps: 0 geff calls, 1 theta_from_h, 2 h_from_se,
+   * 3 k_from_se, 4 se_from_h, 5 theta root-finder iterations, 6 column-mass iterations,
+   * 7 sub-steps.  Used for the algorithmic FLOP count of the roofline.            */
+  unsigned long long* counters; /* [8]                                                          */
+} lgar_outputs;
+
+/* Library / device probe.  Returns 0 if an sm_100 device is current and usable.               */
+int lgar_abi_version(void);
+int lgar_device_check(void);
+const char* lgar_last_error_string(void);
+
+/* Bytes of device workspace needed by lgar_forward/lgar_backward for this problem shape
+ * (only B, L, T, S, max_fronts, chunk_steps are read).  `with_grad` != 0 adds the checkpoint
+ * store and the reverse-sweep scratch.                                                         */
+size_t lgar_workspace_bytes(const lgar_problem* p, int with_grad);
+
+/* Forward: advance all B columns through all T forcing steps in ONE persistent launch.
+ * If `workspace_dev` was sized with with_grad != 0, state checkpoints for lgar_backward are
+ * stored in it (pass keep_checkpoints != 0).                                                   */
+int lgar_forward(const lgar_problem* p, const lgar_outputs* out, void* workspace_dev,
+                 size_t workspace_bytes, int keep_checkpoints, void* stream);
+
+/* Reverse mode.  grad_per_step[NOUT][T][B] (rows selected by grad_mask) and/or
+ * grad_sums[NOUT][B] are dL/d(output); writes dL/d(alpha,n,ksat) as [L][B] arrays.
+ * Must follow an lgar_forward with keep_checkpoints on the same workspace and problem.         */
+int lgar_backward(const lgar_problem* p, const double* grad_per_step, uint32_t grad_mask,
+                  const double* grad_sums, double* grad_alpha, double* grad_n, double* grad_ksat,
+                  void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Convenience for non-CUDA hosts: same as lgar_forward but every pointer in `p` and `out` is a
+ * HOST pointer; the library allocates device memory, copies in, runs, copies out, synchronises. */
+int lgar_forward_host(const lgar_problem* p, const lgar_outputs* out);
+
+/* FP64 peak probe used by bench.py for the roofline denominator: runs a dependent-chain-free
+ * DFMA kernel for `iters` iterations on the current device and returns achieved FLOP/s
+ * (0 on failure).  Synchronous.                                                                */
+double lgar_measure_fp64_flops(int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGAR_B200_H */

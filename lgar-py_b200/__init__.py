@@ -1,0 +1,13 @@
+"""lgar_b200 -- B200-native time-stepping core of dpLGAR (hand-written sm_100a CUDA behind a C ABI).
+
+Public surface:
+  ColumnEnsemble, lgar_columns, forward_raw   batched columns (columns.py)
+  dpLGAR                                      drop-in nn.Module mirroring the reference model API
+  _capi                                       ctypes binding of include/lgar_b200.h
+"""
+from . import _capi
+from ._capi import OUT_NAMES, STATUS_NAMES, LGARLibraryError
+from .columns import ColumnEnsemble, ForwardResult, forward_raw, lgar_columns, output_mask
+
+__all__ = ["ColumnEnsemble", "ForwardResult", "forward_raw", "lgar_columns", "output_mask", "OUT_NAMES",
+           "STATUS_NAMES", "LGARLibraryError", "_capi"]

@@ -1,0 +1,246 @@
+"""Batched LGAR columns on one B200: the torch-facing wrapper around the C ABI.
+
+`ColumnEnsemble` holds what the reference keeps in `cfg` + `GlobalParams`
+(dpLGAR/models/physics/GlobalParams.py:79-138) for B independent columns;
+`lgar_columns(alpha, n, ksat, ens)` is the batched equivalent of running
+`dpLGAR.forward(x[t])` for every row of the forcing record
+(dpLGAR/agents/DifferentiableLGAR.py:117-125) and is differentiable in alpha/n/ksat through the
+hand-written reverse-mode kernel (reference autograd semantics).
+
+PyTorch is used for device memory, streams and autograd plumbing only; all arithmetic happens
+in liblgar_b200.so.  There is no CPU path: tensors are moved to the CUDA device (H2D) if they
+arrive on the host, and the call fails loudly if the library or an sm_100 GPU is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import torch
+
+from . import _capi
+from ._capi import NUM_OUTPUTS, OUT_NAMES, MAX_FRONTS
+
+F64 = torch.float64
+
+
+def _dev_f64(x, device, shape=None):
+    t = torch.as_tensor(x, dtype=F64)
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        if t.dim() == 1 and len(shape) == 2 and t.shape[0] == shape[0]:
+            t = t.unsqueeze(1)  # per-layer values shared by all columns
+        t = t.expand(shape)
+    return t.to(device, non_blocking=True).contiguous()
+
+
+@dataclass
+class ColumnEnsemble:
+    """Static description of B soil columns with L layers each (everything except alpha/n/ksat).
+
+    Array layouts follow the C ABI: `[L, B]` (layer-major, column fastest)."""
+    theta_r: torch.Tensor           # [L,B]
+    theta_e: torch.Tensor           # [L,B]
+    thickness: torch.Tensor         # [L,B] cm
+    forcing: torch.Tensor           # [sites,T,2] (P, PET) cm/h, or [T,2]
+    site_index: Optional[torch.Tensor] = None   # [B] int32
+    initial_psi: object = 2000.0    # scalar or [B]
+    ponded_depth_max: object = 0.0  # scalar or [B]
+    subcycle_length_h: float = 1.0
+    num_subcycles: int = 1
+    nint: int = 120
+    wilting_point_psi: float = 15495.0
+    frozen_factor: float = 1.0
+    giuh_ordinates: Sequence[float] = (0.06, 0.51, 0.28, 0.12, 0.03)
+    max_fronts: int = 16
+    chunk_steps: int = 64
+    iter_cap: int = 0
+    device: object = "cuda"
+    _keep: list = field(default_factory=list, repr=False)
+
+    def __post_init__(self):
+        dev = torch.device(self.device)
+        if dev.type != "cuda":
+            raise _capi.LGARLibraryError("lgar_b200 has no CPU path: device must be a CUDA device")
+        self.device = dev
+        self.theta_r = _dev_f64(self.theta_r, dev)
+        L, B = self.theta_r.shape
+        self.theta_e = _dev_f64(self.theta_e, dev, (L, B))
+        self.thickness = _dev_f64(self.thickness, dev, (L, B))
+        f = torch.as_tensor(self.forcing, dtype=F64)
+        if f.dim() == 2:
+            f = f.unsqueeze(0)
+        assert f.dim() == 3 and f.shape[2] == 2, "forcing must be [sites,T,2]"
+        self.forcing = f.to(dev, non_blocking=True).contiguous()
+        if self.site_index is not None:
+            self.site_index = torch.as_tensor(self.site_index, dtype=torch.int32).to(dev).contiguous()
+            assert self.site_index.shape == (B,)
+        self.initial_psi = _dev_f64(self.initial_psi, dev, (B,))
+        self.ponded_depth_max = _dev_f64(self.ponded_depth_max, dev, (B,))
+
+    @property
+    def num_layers(self): return self.theta_r.shape[0]
+    @property
+    def num_columns(self): return self.theta_r.shape[1]
+    @property
+    def num_steps(self): return self.forcing.shape[1]
+
+    def problem(self, alpha, n, ksat) -> _capi.Problem:
+        p = _capi.Problem()
+        p.abi_version = _capi.ABI_VERSION
+        p.num_columns, p.num_layers, p.num_steps = self.num_columns, self.num_layers, self.num_steps
+        p.num_subcycles, p.num_sites = int(self.num_subcycles), self.forcing.shape[0]
+        p.nint, p.num_giuh = int(self.nint), len(self.giuh_ordinates)
+        p.max_fronts, p.chunk_steps, p.iter_cap = int(self.max_fronts), int(self.chunk_steps), int(self.iter_cap)
+        p.subcycle_length_h = float(self.subcycle_length_h)
+        p.wilting_point_psi = float(self.wilting_point_psi)
+        p.frozen_factor = float(self.frozen_factor)
+        for i, g in enumerate(self.giuh_ordinates):
+            p.giuh_ordinates[i] = float(g)
+        p.alpha, p.n, p.ksat = alpha.data_ptr(), n.data_ptr(), ksat.data_ptr()
+        p.theta_r, p.theta_e, p.thickness = self.theta_r.data_ptr(), self.theta_e.data_ptr(), self.thickness.data_ptr()
+        p.initial_psi, p.ponded_depth_max = self.initial_psi.data_ptr(), self.ponded_depth_max.data_ptr()
+        p.forcing = self.forcing.data_ptr()
+        p.site_index = self.site_index.data_ptr() if self.site_index is not None else None
+        return p
+
+
+def output_mask(names) -> int:
+    m = 0
+    for nme in names:
+        m |= 1 << OUT_NAMES.index(nme)
+    return m
+
+
+@dataclass
+class ForwardResult:
+    per_step: Optional[torch.Tensor]   # [NOUT,T,B]; only rows in `mask` are defined
+    mask: int
+    sums: torch.Tensor                 # [NOUT,B]
+    start_volume: torch.Tensor         # [B]
+    status: torch.Tensor               # [B] int32
+    crash_step: torch.Tensor           # [B] int32
+    num_fronts: Optional[torch.Tensor] = None      # [T,B]
+    fronts: Optional[torch.Tensor] = None          # [T,16,5,B]
+    front_layer: Optional[torch.Tensor] = None     # [T,16,B]
+    front_to_bottom: Optional[torch.Tensor] = None # [T,16,B]
+    counters: Optional[torch.Tensor] = None        # [8] int64
+
+    def __getitem__(self, name) -> torch.Tensor:
+        k = OUT_NAMES.index(name)
+        assert self.per_step is not None and (self.mask >> k) & 1, f"output {name} was not requested"
+        return self.per_step[k]
+
+
+def _param(x, ens: ColumnEnsemble):
+    t = torch.as_tensor(x, dtype=F64)
+    if t.dim() == 1:  # one parameter set shared by all columns
+        t = t.unsqueeze(1).expand(ens.num_layers, ens.num_columns)
+    return t.to(ens.device, non_blocking=True).contiguous()
+
+
+def forward_raw(ens: ColumnEnsemble, alpha, n, ksat, outputs=("runoff", "percolation"), per_step=True,
+                num_fronts=False, dump_fronts=False, counters=False, keep_checkpoints=False,
+                workspace: Optional[torch.Tensor] = None) -> tuple[ForwardResult, torch.Tensor]:
+    """One persistent launch over all columns and all forcing steps (no autograd)."""
+    L_ = _capi.lib()
+    dev = ens.device
+    alpha, n, ksat = _param(alpha, ens), _param(n, ens), _param(ksat, ens)
+    B, T = ens.num_columns, ens.num_steps
+    p = ens.problem(alpha, n, ksat)
+    need = L_.lgar_workspace_bytes(C.byref(p), 1 if keep_checkpoints else 0)
+    if need == 0:
+        _capi.check(-1, "lgar_workspace_bytes")
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+    mask = output_mask(outputs) if per_step else 0
+    o = _capi.Outputs()
+    res = ForwardResult(
+        per_step=torch.zeros((NUM_OUTPUTS, T, B), dtype=F64, device=dev) if mask else None, mask=mask,
+        sums=torch.empty((NUM_OUTPUTS, B), dtype=F64, device=dev),
+        start_volume=torch.empty(B, dtype=F64, device=dev),
+        status=torch.empty(B, dtype=torch.int32, device=dev),
+        crash_step=torch.empty(B, dtype=torch.int32, device=dev))
+    o.per_step = res.per_step.data_ptr() if mask else None
+    o.per_step_mask = mask
+    o.sums, o.start_volume = res.sums.data_ptr(), res.start_volume.data_ptr()
+    o.status, o.crash_step = res.status.data_ptr(), res.crash_step.data_ptr()
+    if num_fronts or dump_fronts:
+        res.num_fronts = torch.empty((T, B), dtype=torch.int32, device=dev)
+        o.num_fronts = res.num_fronts.data_ptr()
+    if dump_fronts:
+        res.fronts = torch.empty((T, MAX_FRONTS, 5, B), dtype=F64, device=dev)
+        res.front_layer = torch.empty((T, MAX_FRONTS, B), dtype=torch.int8, device=dev)
+        res.front_to_bottom = torch.empty((T, MAX_FRONTS, B), dtype=torch.int8, device=dev)
+        o.fronts, o.front_layer = res.fronts.data_ptr(), res.front_layer.data_ptr()
+        o.front_to_bottom = res.front_to_bottom.data_ptr()
+    if counters or dump_fronts:
+        res.counters = torch.zeros(8, dtype=torch.int64, device=dev)
+        o.counters = res.counters.data_ptr()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        rc = L_.lgar_forward(C.byref(p), C.byref(o), workspace.data_ptr(), workspace.numel(),
+                             1 if keep_checkpoints else 0, C.c_void_p(stream))
+    _capi.check(rc, "lgar_forward")
+    res._keep = (alpha, n, ksat, ens)  # keep inputs alive until the stream has consumed them
+    return res, workspace
+
+
+class _LGARFunction(torch.autograd.Function):
+    """autograd bridge: forward = lgar_forward (stores chunk checkpoints), backward = lgar_backward."""
+
+    @staticmethod
+    def forward(ctx, alpha, n, ksat, ens: ColumnEnsemble, mask: int):
+        outputs = [OUT_NAMES[k] for k in range(NUM_OUTPUTS) if (mask >> k) & 1]
+        need_grad = any(ctx.needs_input_grad[:3])
+        res, ws = forward_raw(ens, alpha.detach(), n.detach(), ksat.detach(), outputs=outputs,
+                              keep_checkpoints=need_grad)
+        ctx.ens, ctx.mask, ctx.ws = ens, mask, ws
+        ctx.save_for_backward(*res._keep[:3])
+        ctx.in_shapes = (alpha.shape, n.shape, ksat.shape)
+        ctx.mark_non_differentiable(res.status, res.crash_step, res.start_volume)
+        per_step = res.per_step if res.per_step is not None else torch.zeros(0, dtype=F64, device=ens.device)
+        return per_step, res.sums, res.start_volume, res.status, res.crash_step
+
+    @staticmethod
+    def backward(ctx, g_per_step, g_sums, _gsv, _gst, _gcs):
+        L_ = _capi.lib()
+        ens: ColumnEnsemble = ctx.ens
+        alpha, n, ksat = ctx.saved_tensors
+        dev = ens.device
+        Lr, B = ens.num_layers, ens.num_columns
+        p = ens.problem(alpha, n, ksat)
+        ga = torch.zeros((Lr, B), dtype=F64, device=dev)
+        gn = torch.zeros_like(ga)
+        gk = torch.zeros_like(ga)
+        gps = g_per_step.contiguous() if (g_per_step is not None and g_per_step.numel()) else None
+        gs = g_sums.contiguous() if g_sums is not None else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            rc = L_.lgar_backward(C.byref(p), gps.data_ptr() if gps is not None else None, ctx.mask,
+                                  gs.data_ptr() if gs is not None else None, ga.data_ptr(), gn.data_ptr(),
+                                  gk.data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(), C.c_void_p(stream))
+        _capi.check(rc, "lgar_backward")
+
+        def shape_back(g, shp):
+            return g.sum(dim=1) if len(shp) == 1 else g
+        sa, sn, sk = ctx.in_shapes
+        return shape_back(ga, sa), shape_back(gn, sn), shape_back(gk, sk), None, None
+
+
+def lgar_columns(alpha, n, ksat, ens: ColumnEnsemble, outputs=("runoff", "percolation")):
+    """Differentiable batched run.  alpha/n/ksat: `[L,B]` (per column) or `[L]` (shared).
+    Returns a dict: every requested output as `[T,B]`, plus `sums[NOUT,B]`, `start_volume[B]`,
+    `status[B]`, `crash_step[B]`."""
+    mask = output_mask(outputs)
+    dev = ens.device
+    a = torch.as_tensor(alpha, dtype=F64).to(dev)
+    nn_ = torch.as_tensor(n, dtype=F64).to(dev)
+    k = torch.as_tensor(ksat, dtype=F64).to(dev)
+    ae = a if a.dim() == 2 else a.unsqueeze(1).expand(ens.num_layers, ens.num_columns)
+    ne = nn_ if nn_.dim() == 2 else nn_.unsqueeze(1).expand(ens.num_layers, ens.num_columns)
+    ke = k if k.dim() == 2 else k.unsqueeze(1).expand(ens.num_layers, ens.num_columns)
+    per_step, sums, sv, st, cs = _LGARFunction.apply(ae.contiguous(), ne.contiguous(), ke.contiguous(), ens, mask)
+    out = {name: per_step[OUT_NAMES.index(name)] for name in outputs}
+    out.update(sums=sums, start_volume=sv, status=st, crash_step=cs)
+    return out

@@ -1,0 +1,299 @@
+// =====================================================================================
+// lgar_capi.cu -- extern "C" entry points declared in include/lgar_b200.h.
+// Host-side only does argument checking, workspace carving and ONE kernel launch per call.
+// There is no CPU fallback: without an sm_100 device every compute entry point fails.
+// =====================================================================================
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "lgar_forward.cuh"
+#ifdef LGAR_WITH_BACKWARD
+#include "lgar_backward.cuh"
+#endif
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* detail = "") {
+  std::snprintf(g_err, sizeof(g_err), fmt, detail);
+  return code;
+}
+#define CUDA_TRY(expr)                                                         \
+  do {                                                                         \
+    cudaError_t e__ = (expr);                                                  \
+    if (e__ != cudaSuccess) {                                                  \
+      std::snprintf(g_err, sizeof(g_err), "%s failed: %s", #expr, cudaGetErrorString(e__)); \
+      return LGAR_E_CUDA;                                                      \
+    }                                                                          \
+  } while (0)
+
+struct Shape {
+  int B, Bp, L, T, S, FM, chunk, nchunks, ntiles;
+};
+
+int shape_of(const lgar_problem* p, Shape& s) {
+  if (!p) return fail(LGAR_E_INVALID, "problem is NULL");
+  if (p->abi_version != LGAR_ABI_VERSION) return fail(LGAR_E_INVALID, "abi_version mismatch");
+  if (p->num_columns < 1 || p->num_steps < 1 || p->num_subcycles < 1) return fail(LGAR_E_INVALID, "empty problem");
+  if (p->num_layers < 1 || p->num_layers > LGAR_MAX_LAYERS) return fail(LGAR_E_INVALID, "num_layers out of range");
+  if (p->nint < 1 || p->nint > 128) return fail(LGAR_E_INVALID, "nint must be in [1,128]");
+  if (p->num_giuh < 1 || p->num_giuh > LGAR_MAX_GIUH) return fail(LGAR_E_INVALID, "num_giuh out of range");
+  s.B = p->num_columns;
+  s.Bp = (s.B + 31) / 32 * 32;
+  s.L = p->num_layers;
+  s.T = p->num_steps;
+  s.S = p->num_subcycles;
+  s.FM = p->max_fronts == 0 ? 16 : p->max_fronts;
+  if (s.FM != 8 && s.FM != 12 && s.FM != 16) return fail(LGAR_E_INVALID, "max_fronts must be 8, 12 or 16");
+  s.chunk = p->chunk_steps > 0 ? p->chunk_steps : 64;
+  s.nchunks = (s.T + s.chunk - 1) / s.chunk;
+  s.ntiles = s.Bp / 32;
+  return 0;
+}
+
+size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct Carve {
+  size_t off_d, off_i, off_f, off_done, off_item, total;
+};
+
+Carve carve(const Shape& s, int with_grad) {
+  const size_t nck = with_grad ? (size_t)s.nchunks + 1 : 1;
+  const size_t nd = 5 * (size_t)s.FM + lgar::S_COUNT;
+  Carve c;
+  size_t o = 0;
+  c.off_d = o;   o = align_up(o + nck * nd * s.Bp * sizeof(double));
+  c.off_i = o;   o = align_up(o + nck * lgar::NI_STATE * s.Bp * sizeof(int32_t));
+  c.off_f = o;   o = align_up(o + nck * (size_t)s.FM * s.Bp);
+  c.off_done = o; o = align_up(o + (size_t)s.ntiles * sizeof(int32_t));
+  c.off_item = o; o = align_up(o + 64);
+  c.total = o;
+  return c;
+}
+
+int g_dev_checked = -2;
+int g_num_sms = 0;
+
+template <int FM>
+size_t smem_bytes() {
+  return (size_t)5 * FM * lgar::NT * sizeof(double) + (size_t)lgar::WARPS * lgar::NODEBUF * sizeof(double) +
+         (size_t)FM * lgar::NT;
+}
+
+template <int FM, bool COUNT, bool DUMP>
+int launch_forward(const lgar::KParams& K, cudaStream_t st) {
+  auto kern = lgar::lgar_forward_kernel<FM, COUNT, DUMP>;
+  const size_t smem = smem_bytes<FM>();
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, lgar::NT, smem));
+  if (per_sm < 1) return fail(LGAR_E_CUDA, "forward kernel does not fit on an SM");
+  long long want = ((long long)K.ntiles * K.nchunks + lgar::WARPS - 1) / lgar::WARPS;
+  long long grid = (long long)g_num_sms * per_sm;
+  if (grid > want) grid = want;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, lgar::NT, smem, st>>>(K);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+// ---- host-buffer variant ------------------------------------------------------------
+namespace {
+struct DevBuf {
+  std::vector<void*> ptrs;
+  ~DevBuf() {
+    for (void* p : ptrs) cudaFree(p);
+  }
+  template <class T>
+  int up(const T* host, size_t count, const T** dev_out) {
+    *dev_out = nullptr;
+    if (!host) return 0;
+    void* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, count * sizeof(T)));
+    ptrs.push_back(d);
+    CUDA_TRY(cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *dev_out = (const T*)d;
+    return 0;
+  }
+  template <class T>
+  int alloc(const T* host, size_t count, T** dev_out) {
+    *dev_out = nullptr;
+    if (!host) return 0;
+    void* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, count * sizeof(T)));
+    ptrs.push_back(d);
+    *dev_out = (T*)d;
+    return 0;
+  }
+};
+}  // namespace
+
+
+extern "C" {
+
+int lgar_abi_version(void) { return LGAR_ABI_VERSION; }
+
+const char* lgar_last_error_string(void) { return g_err; }
+
+int lgar_device_check(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(LGAR_E_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) return fail(LGAR_E_NO_DEVICE, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10) return fail(LGAR_E_NO_DEVICE, "device is not sm_100 (B200): %s", prop.name);
+  g_num_sms = prop.multiProcessorCount;
+  g_dev_checked = dev;
+  return 0;
+}
+
+size_t lgar_workspace_bytes(const lgar_problem* p, int with_grad) {
+  Shape s;
+  if (shape_of(p, s)) return 0;
+  size_t total = carve(s, with_grad).total;
+#ifdef LGAR_WITH_BACKWARD
+  if (with_grad) total += lgar::backward_scratch_bytes(s.B, s.Bp, s.L, s.S, s.FM, s.chunk);
+#endif
+  return total;
+}
+
+int lgar_forward(const lgar_problem* p, const lgar_outputs* out, void* workspace_dev, size_t workspace_bytes,
+                 int keep_checkpoints, void* stream) {
+  Shape s;
+  int rc = shape_of(p, s);
+  if (rc) return rc;
+  if (!out) return fail(LGAR_E_INVALID, "outputs is NULL");
+  if (!p->alpha || !p->n || !p->ksat || !p->theta_r || !p->theta_e || !p->thickness || !p->initial_psi ||
+      !p->ponded_depth_max || !p->forcing)
+    return fail(LGAR_E_INVALID, "a required problem array is NULL");
+  if (p->num_sites < 1) return fail(LGAR_E_INVALID, "num_sites < 1");
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev != g_dev_checked) {
+    rc = lgar_device_check();
+    if (rc) return rc;
+  }
+  const Carve c = carve(s, keep_checkpoints);
+  if (!workspace_dev || workspace_bytes < c.total) return fail(LGAR_E_WORKSPACE, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* w = (unsigned char*)workspace_dev;
+
+  lgar::KParams K;
+  std::memset(&K, 0, sizeof(K));
+  K.p = *p;
+  K.o = *out;
+  K.state_d = (double*)(w + c.off_d);
+  K.state_i = (int32_t*)(w + c.off_i);
+  K.state_f = (uint8_t*)(w + c.off_f);
+  K.done = (int32_t*)(w + c.off_done);
+  K.next_item = (unsigned long long*)(w + c.off_item);
+  K.Bp = s.Bp;
+  K.ntiles = s.ntiles;
+  K.nchunks = s.nchunks;
+  K.chunk_steps = s.chunk;
+  K.keep_ckpt = keep_checkpoints ? 1 : 0;
+  K.iter_cap = p->iter_cap > 0 ? p->iter_cap : 1000000;
+  CUDA_TRY(cudaMemsetAsync(w + c.off_done, 0, c.total - c.off_done, st));
+  if (out->counters) CUDA_TRY(cudaMemsetAsync(out->counters, 0, 8 * sizeof(unsigned long long), st));
+  const bool count = out->counters != nullptr;
+  const bool dump = out->fronts != nullptr;
+#define LGAR_DISPATCH(FM_)                                                         \
+  if (dump) rc = launch_forward<FM_, true, true>(K, st);                           \
+  else if (count) rc = launch_forward<FM_, true, false>(K, st);                    \
+  else rc = launch_forward<FM_, false, false>(K, st);
+  if (s.FM == 8) { LGAR_DISPATCH(8) }
+  else if (s.FM == 12) { LGAR_DISPATCH(12) }
+  else { LGAR_DISPATCH(16) }
+#undef LGAR_DISPATCH
+  return rc;
+}
+
+#ifndef LGAR_WITH_BACKWARD
+int lgar_backward(const lgar_problem*, const double*, uint32_t, const double*, double*, double*, double*, void*,
+                  size_t, void*) {
+  return fail(LGAR_E_INVALID, "library built without the reverse-mode kernel");
+}
+#endif
+
+int lgar_forward_host(const lgar_problem* ph, const lgar_outputs* oh) {
+  Shape s;
+  int rc = shape_of(ph, s);
+  if (rc) return rc;
+  if (!oh) return fail(LGAR_E_INVALID, "outputs is NULL");
+  rc = lgar_device_check();
+  if (rc) return rc;
+  DevBuf db;
+  lgar_problem p = *ph;
+  lgar_outputs o = *oh;
+  const size_t LB = (size_t)s.L * s.B, B = s.B, T = s.T;
+#define UP(field, count) if ((rc = db.up(ph->field, (count), &p.field))) return rc;
+  UP(alpha, LB) UP(n, LB) UP(ksat, LB) UP(theta_r, LB) UP(theta_e, LB) UP(thickness, LB)
+  UP(initial_psi, B) UP(ponded_depth_max, B) UP(forcing, (size_t)ph->num_sites * T * 2) UP(site_index, B)
+#undef UP
+#define AL(field, count) if ((rc = db.alloc(oh->field, (count), &o.field))) return rc;
+  AL(per_step, (size_t)LGAR_NUM_OUTPUTS * T * B) AL(sums, (size_t)LGAR_NUM_OUTPUTS * B) AL(start_volume, B)
+  AL(status, B) AL(crash_step, B) AL(num_fronts, T * B) AL(fronts, T * LGAR_MAX_FRONTS * 5 * B)
+  AL(front_layer, T * LGAR_MAX_FRONTS * B) AL(front_to_bottom, T * LGAR_MAX_FRONTS * B) AL(counters, 8)
+#undef AL
+  if (o.per_step) CUDA_TRY(cudaMemset(o.per_step, 0, (size_t)LGAR_NUM_OUTPUTS * T * B * sizeof(double)));
+  const size_t wsb = lgar_workspace_bytes(&p, 0);
+  void* ws = nullptr;
+  CUDA_TRY(cudaMalloc(&ws, wsb));
+  db.ptrs.push_back(ws);
+  rc = lgar_forward(&p, &o, ws, wsb, 0, nullptr);
+  if (rc) return rc;
+  CUDA_TRY(cudaDeviceSynchronize());
+#define DOWN(field, count) \
+  if (oh->field) CUDA_TRY(cudaMemcpy(oh->field, o.field, (count) * sizeof(*oh->field), cudaMemcpyDeviceToHost));
+  DOWN(per_step, (size_t)LGAR_NUM_OUTPUTS * T * B) DOWN(sums, (size_t)LGAR_NUM_OUTPUTS * B) DOWN(start_volume, B)
+  DOWN(status, B) DOWN(crash_step, B) DOWN(num_fronts, T * B) DOWN(fronts, T * LGAR_MAX_FRONTS * 5 * B)
+  DOWN(front_layer, T * LGAR_MAX_FRONTS * B) DOWN(front_to_bottom, T * LGAR_MAX_FRONTS * B) DOWN(counters, 8)
+#undef DOWN
+  return 0;
+}
+
+}  // extern "C"
+
+// ---- FP64 peak probe ------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) dfma_probe(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-9, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0;
+  double x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0, x7 = x0 + 7.0;
+  for (int i = 0; i < iters; i++) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+}  // namespace
+
+extern "C" double lgar_measure_fp64_flops(int iters) {
+  if (lgar_device_check()) return 0.0;
+  if (iters < 1) iters = 4096;
+  const int blocks = g_num_sms * 8, threads = 256;
+  double* d = nullptr;
+  if (cudaMalloc(&d, (size_t)blocks * threads * sizeof(double)) != cudaSuccess) return 0.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  dfma_probe<<<blocks, threads>>>(d, iters, 0.999999, 1e-7);  // warm-up
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0);
+    dfma_probe<<<blocks, threads>>>(d, iters, 0.999999, 1e-7);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) break;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3);
+    if (flops > best) best = flops;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  return best;
+}

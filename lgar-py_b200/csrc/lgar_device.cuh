@@ -1,0 +1,775 @@
+// =====================================================================================
+// lgar_device.cuh -- device-side LGAR column physics for sm_100a (fp64).
+//
+// One THREAD owns one soil column; one WARP owns a tile of 32 columns.  The variable-length
+// wetting-front list of every column lives in shared memory as a flat array
+// (field-major, thread fastest: element (field f, front i, thread t) at (f*FM + i)*NT + t,
+// which is bank-conflict free for ANY per-lane front index).  The reference keeps one Python
+// list per soil layer; here the global order is the concatenation of those lists and the
+// per-layer list lengths are kept in `cnt` (list membership) separately from the front's own
+// `layer_num` attribute, because the reference lets the two disagree transiently while a front
+// crosses a layer boundary (physics/layers/Layer.py:965-1008 then :951-963).
+//
+// The Green-Ampt capillary drive Geff (physics/lgar/green_ampt.py:19-99; 120-interval
+// trapezoid = 480 pow) is evaluated WARP-COOPERATIVELY: lanes = trapezoid nodes, so its cost
+// does not depend on how many lanes of the warp need it (divergent front counts).  The
+// node conductivities are then summed by the requesting lane in the reference's sequential
+// order, so the result is bit-identical to a scalar evaluation.
+//
+// All citations are relative to /root/reference/dpLGAR/.  Quirk numbers (Qn) refer to
+// SURVEY.md section 8(a).
+// =====================================================================================
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/lgar_b200.h"
+
+namespace lgar {
+
+constexpr int NT = 128;          // threads per CTA (4 warps, each warp an independent tile)
+constexpr int WARPS = NT / 32;
+constexpr int NODEBUF = 136;     // doubles of per-warp scratch for Geff nodes (nint <= 128)
+constexpr int MAXL = LGAR_MAX_LAYERS;
+constexpr int NGIUH = LGAR_MAX_GIUH;
+constexpr int NOUT = LGAR_NUM_OUTPUTS;
+
+enum Field { F_DEPTH = 0, F_THETA = 1, F_PSI = 2, F_K = 3, F_DZDT = 4 };
+
+// work counters (per thread, flushed once per chunk when counting is enabled)
+enum Cnt { C_GEFF = 0, C_THETA_H = 1, C_H_SE = 2, C_K_SE = 3, C_SE_H = 4, C_ROOT = 5, C_COLMASS = 6, C_SUB = 7 };
+
+struct Soil {  // one layer of one column: Layer.attributes + alpha/n/ksat (Layer.py:48-57)
+  double alpha, n, m, inv_m, ninv_m, inv_n, ksat, the, thr;
+};
+
+struct Ctx {  // per-thread execution context
+  int st;               // lgar_status, first error wins
+  unsigned cnt[8];      // work counters
+  long long iter_cap;
+};
+
+__device__ __forceinline__ void raise(Ctx& c, int code) {
+  if (c.st == 0) c.st = code;
+}
+
+// ------------------------------------------------------------------------------------
+// van Genuchten closures (physics/utils.py).  pow goes through ONE out-of-line copy of the
+// CUDA math library's pow so that the hot loops stay inside the instruction cache.
+// ------------------------------------------------------------------------------------
+__device__ __noinline__ double pow_f64(double a, double b) { return pow(a, b); }
+
+// utils.py:12-32 safe_pow: NaN input or negative base raise ValueError
+__device__ __forceinline__ double safe_pow(double base, double e, Ctx& c) {
+  if (isnan(base) || isnan(e)) raise(c, LGAR_ST_NAN);
+  else if (base < 0.0) raise(c, LGAR_ST_NEG_POW);
+  return pow_f64(base, e);
+}
+__device__ __forceinline__ double error_check(double r, Ctx& c) {  // utils.py:177-185
+  if (isnan(r)) raise(c, LGAR_ST_NAN);
+  return r;
+}
+// utils.py:35-51
+__device__ __forceinline__ double theta_from_h(double h, const Soil& s, Ctx& c) {
+  c.cnt[C_THETA_H]++;
+  double alpha_pow = safe_pow(s.alpha * h, s.n, c);
+  double outer = safe_pow(1.0 + alpha_pow, s.m, c);
+  double r = (1.0 / outer * (s.the - s.thr)) + s.thr;
+  return error_check(r, c);
+}
+// utils.py:102-112
+__device__ __forceinline__ double se_from_theta(double theta, const Soil& s, Ctx& c) {
+  return error_check((theta - s.thr) / (s.the - s.thr), c);
+}
+// utils.py:115-131 (constant 1.0 for |h| < 0.1, Q12)
+__device__ __forceinline__ double se_from_h(double h, const Soil& s, Ctx& c) {
+  c.cnt[C_SE_H]++;
+  if (fabs(h) < 1.0e-01) return 1.0;
+  double internal = safe_pow(s.alpha * h, s.n, c);
+  double r = 1.0 / safe_pow(1.0 + internal, s.m, c);
+  return error_check(r, c);
+}
+// utils.py:134-156.  torch.isclose(base, 0, 1e-12) == |base| <= 1e-8 (Q2); pow(x, 2) == x*x
+// bit-for-bit in glibc (checked over 5e6 samples).
+__device__ __forceinline__ double k_from_se(double se, double ksat, double m, double inv_m, Ctx& c) {
+  c.cnt[C_K_SE]++;
+  double se_pow = safe_pow(se, inv_m, c);
+  double base = 1.0 - se_pow;
+  if (fabs(base) <= 1e-8) base = base + 1e-12;
+  double outside = safe_pow(base, m, c);
+  double t = 1.0 - outside;
+  if (isnan(t)) raise(c, LGAR_ST_NAN);
+  else if (t < 0.0) raise(c, LGAR_ST_NEG_POW);
+  double r = ksat * sqrt(se) * (t * t);
+  return error_check(r, c);
+}
+// utils.py:159-174
+__device__ __forceinline__ double h_from_se(double se, const Soil& s, Ctx& c) {
+  c.cnt[C_H_SE]++;
+  double se_pow = safe_pow(se, s.ninv_m, c);
+  double base = se_pow - 1.0;
+  if (fabs(base) <= 1e-8) base = base + 1e-12;
+  double outside = safe_pow(base, s.inv_n, c);
+  double r = 1.0 / s.alpha * outside;
+  return error_check(r, c);
+}
+
+// torch.min / torch.minimum semantics (NaN propagates, unlike fmin)
+__device__ __forceinline__ double tmin(double a, double b) {
+  if (isnan(a) || isnan(b)) return a + b;
+  return (b < a) ? b : a;
+}
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// ------------------------------------------------------------------------------------
+// Warp-cooperative Geff (green_ampt.py:19-99, trapezoid branch).
+// Must be called by all 32 lanes of the warp (convergent).  Lanes with need==true get
+// Geff(theta_1, theta_2) for their own soil `s`; the others get 0.
+//   stage A (per lane): Se, h at both ends, dh, K at node 0 -- exactly the reference's scalars
+//   stage B (per request, all lanes): node k = 1..nint has h2_k = h_i + dh + dh ... (k adds, the
+//            same accumulated rounding as `h2 = h2 + dh`), K_k = K(Se(h2_k)); lane j takes
+//            nodes j, j+32, j+64, ...
+//   stage C (requesting lane): geff = sum_i (K_{i-1} + K_i) * (dh / 2) in the reference's order.
+// ------------------------------------------------------------------------------------
+__device__ __noinline__ double geff_warp(bool need, double theta_1, double theta_2, const Soil& s, int nint,
+                                         double* nodebuf, Ctx& c) {
+  const int lane = threadIdx.x & 31;
+  double h_i = 0.0, dh = 0.0, k0 = 0.0;
+  if (need) {
+    c.cnt[C_GEFF]++;
+    double se_i = se_from_theta(theta_1, s, c);
+    double se_f = se_from_theta(theta_2, s, c);
+    h_i = h_from_se(se_i, s, c);
+    double h_f = h_from_se(se_f, s, c);
+    // "Checkpoint" calls green_ampt.py:61-63: results unused, only their guards can matter
+    if (fabs(h_i) >= 0.1 && s.alpha * h_i < 0.0) raise(c, LGAR_ST_NEG_POW);
+    if (fabs(h_f) >= 0.1 && s.alpha * h_f < 0.0) raise(c, LGAR_ST_NEG_POW);
+    dh = (h_f - h_i) / (double)nint;
+    k0 = k_from_se(se_i, s.ksat, s.m, s.inv_m, c);
+  }
+  unsigned mask = __ballot_sync(0xffffffffu, need);
+  double result = 0.0;
+  while (mask) {
+    const int src = __ffs(mask) - 1;
+    mask &= mask - 1;
+    // broadcast the request
+    Soil q;
+    q.alpha = shfl_d(s.alpha, src);
+    q.n = shfl_d(s.n, src);
+    q.m = shfl_d(s.m, src);
+    q.inv_m = shfl_d(s.inv_m, src);
+    q.ksat = shfl_d(s.ksat, src);
+    const double qh = shfl_d(h_i, src);
+    const double qdh = shfl_d(dh, src);
+    const double qk0 = shfl_d(k0, src);
+    Ctx cc;  // guards raised while evaluating nodes are reported to the requesting lane
+    cc.st = 0;
+    double h = qh;
+    int k = 0;
+    for (int target = lane; target <= nint; target += 32) {
+      while (k < target) {  // h2 = h2 + dh, k times
+        h = h + qdh;
+        k++;
+      }
+      double kk;
+      if (target == 0) {
+        kk = qk0;
+      } else {
+        double se2 = se_from_h(h, q, cc);
+        kk = k_from_se(se2, q.ksat, q.m, q.inv_m, cc);
+      }
+      nodebuf[target] = kk;
+    }
+    unsigned bad = __ballot_sync(0xffffffffu, cc.st != 0);
+    int st_any = 0;
+    if (bad) {
+      int b = __ffs(bad) - 1;  // lowest node raises first in the sequential reference
+      st_any = __shfl_sync(0xffffffffu, cc.st, b);
+    }
+    __syncwarp();
+    if (lane == src) {
+      if (st_any) raise(c, st_any);
+      c.cnt[C_SE_H] += nint;
+      c.cnt[C_K_SE] += nint;
+      const double half = qdh / 2.0;
+      double geff = 0.0;
+      double k1 = nodebuf[0];
+#pragma unroll 8
+      for (int i = 1; i <= nint; i++) {
+        double k2 = nodebuf[i];
+        geff = geff + ((k1 + k2) * half);
+        k1 = k2;
+      }
+      result = fabs(geff / s.ksat);
+    }
+    __syncwarp();
+  }
+  return result;
+}
+
+// ------------------------------------------------------------------------------------
+// Column: per-thread view of the front list in shared memory + scalar state in registers
+// ------------------------------------------------------------------------------------
+template <int FM>
+struct Column {
+  double* fb;        // this thread's slot in the field array
+  uint8_t* gb;       // this thread's slot in the flag array: bits 0-2 layer_num attr, bit 7 to_bottom
+  int L;             // number of layers
+  int n;             // total number of fronts
+  unsigned cntpk;    // per-layer list lengths, 8 bits each
+  Soil soil[MAXL];
+  double cum[MAXL];  // cumulative layer thickness (GlobalParams.py:103-110)
+  double thick[MAXL];
+  double pdm;        // ponded_depth_max
+  double psi_wp;     // AET: capillary head at which AET = 0.5 PET (aet.py:37-43); column constant
+  double ponded_water, previous_precip, ending_volume;
+  double giuh[NGIUH];
+
+  __device__ __forceinline__ double& f(int fld, int i) { return fb[(fld * FM + i) * NT]; }
+  __device__ __forceinline__ int lay(int i) const { return gb[i * NT] & 7; }
+  __device__ __forceinline__ bool tb(int i) const { return (gb[i * NT] & 0x80) != 0; }
+  __device__ __forceinline__ void set_flag(int i, int layer, bool to_bottom) {
+    gb[i * NT] = (uint8_t)((layer & 7) | (to_bottom ? 0x80 : 0));
+  }
+  __device__ __forceinline__ int cnt(int l) const { return (cntpk >> (8 * l)) & 0xff; }
+  __device__ __forceinline__ void add_cnt(int l, int d) { cntpk += (unsigned)d << (8 * l); }
+  __device__ __forceinline__ int off(int l) const {
+    int o = 0;
+    for (int k = 0; k < l; k++) o += cnt(k);
+    return o;
+  }
+  __device__ __forceinline__ int list_layer(int i) const {  // which per-layer list holds flat index i
+    int o = 0;
+    for (int l = 0; l < L - 1; l++) {
+      o += cnt(l);
+      if (i < o) return l;
+    }
+    return L - 1;
+  }
+  __device__ __forceinline__ void copy_front(int dst, int src) {
+#pragma unroll
+    for (int k = 0; k < 5; k++) f(k, dst) = f(k, src);
+    gb[dst * NT] = gb[src * NT];
+  }
+  // list.insert(0, front) on layer list l
+  __device__ __forceinline__ bool insert_at(int pos, int l, Ctx& c) {
+    if (n >= FM) {
+      raise(c, LGAR_ST_FRONT_OVERFLOW);
+      return false;
+    }
+    for (int i = n; i > pos; i--) copy_front(i, i - 1);
+    n++;
+    add_cnt(l, 1);
+    return true;
+  }
+  // list.pop(i) on the list holding flat index pos
+  __device__ __forceinline__ void erase_at(int pos, int l) {
+    for (int i = pos; i < n - 1; i++) copy_front(i, i + 1);
+    n--;
+    add_cnt(l, -1);
+  }
+  // WettingFront.is_equal (WettingFront.py:76-84): value equality on depth, psi, dzdt (Q3)
+  __device__ __forceinline__ bool is_equal(int a, int b) {
+    return f(F_DEPTH, a) == f(F_DEPTH, b) && f(F_PSI, a) == f(F_PSI, b) && f(F_DZDT, a) == f(F_DZDT, b);
+  }
+  // Layer.get_len_layers (Layer.py:1145-1155)
+  __device__ __forceinline__ int len_layers(int l) const { return (l < L - 1) ? cnt(l) : cnt(l) - 1; }
+
+  // ---- Layer.mass_balance (Layer.py:795-824); association S0 + (S1 + (S2 ...))
+  __device__ double mass_balance() {
+    double s_l[MAXL];
+    int o = 0;
+    for (int l = 0; l < L; l++) {
+      const double base = (l == 0) ? 0.0 : (cum[l] - thick[l]);
+      const int nf = cnt(l);
+      double sum = 0.0;
+      for (int i = 0; i < nf - 1; i++)
+        sum = sum + (f(F_DEPTH, o + i) - base) * (f(F_THETA, o + i) - f(F_THETA, o + i + 1));
+      sum = sum + (f(F_DEPTH, o + nf - 1) - base) * f(F_THETA, o + nf - 1);
+      s_l[l] = sum;
+      o += nf;
+    }
+    double tot = s_l[L - 1];
+    for (int l = L - 2; l >= 0; l--) tot = s_l[l] + tot;
+    return tot;
+  }
+
+  // ---- free-drainage front (models/dpLGAR.py:328-338, Layer.py:134-162): arg-min psi, ties ->
+  //      deeper; else-branch torch.isclose(psi_i, psi, atol=1e-8) with default rtol 1e-5
+  __device__ int free_drainage_front() {
+    int w = 0;
+    double psi = f(F_PSI, 0);
+    for (int i = 0; i < n; i++) {
+      const double p = f(F_PSI, i);
+      if (p <= psi) {
+        psi = p;
+        w = i;
+      } else {
+        bool close;
+        if (isfinite(p) && isfinite(psi)) close = fabs(p - psi) <= 1e-8 + 1e-5 * fabs(psi);
+        else close = (p == psi);
+        if (close) {
+          psi = p;
+          w = i;
+        }
+      }
+    }
+    return w;
+  }
+
+  // ---- root finder: Layer.theta_mass_balance (Layer.py:242-318) + recalculate_mass (:211-240).
+  //      `lyr` is the layer of the front, `nup` the number of upper layers that take part
+  //      (len(delta_thickness) - 1), dth/dtk the delta_thetas / delta_thickness arrays.
+  __device__ double theta_mass_balance(int lyr, int nup, double psi_cm, double new_mass, double prior_mass,
+                                       const double* dth, const double* dtk, Ctx& c) {
+    const double tol = 1e-12;
+    double delta_mass = fabs(new_mass - prior_mass);
+    bool switched = false;
+    double factor = 1.0;
+    double theta = 0.0;
+    double psi_prev = psi_cm;
+    double delta_mass_prev = delta_mass;
+    int count_no_mass_change = 0;
+    if (delta_mass <= tol) return theta_from_h(psi_cm, soil[lyr], c);
+    long long it = 0;
+    while (delta_mass > tol) {
+      if (++it > c.iter_cap) {
+        raise(c, LGAR_ST_ITER_CAP);
+        break;
+      }
+      c.cnt[C_ROOT]++;
+      if (new_mass > prior_mass) {
+        psi_cm = psi_cm + (0.1 * factor);
+        switched = false;
+      } else {
+        if (!switched) {
+          switched = true;
+          factor = factor * 0.1;
+        }
+        psi_prev = psi_cm;
+        psi_cm = psi_cm - (0.1 * factor);
+        if (psi_cm < 0.0 && psi_prev != 0.0) psi_cm = psi_prev * 0.1;
+      }
+      theta = theta_from_h(psi_cm, soil[lyr], c);
+      double mass_layers = 0.0 + (dtk[lyr] * (theta - dth[lyr]));
+      for (int k = 0; k < nup; k++) {
+        double theta_layer = theta_from_h(psi_cm, soil[k], c);
+        mass_layers = mass_layers + dtk[k] * (theta_layer - dth[k]);
+      }
+      new_mass = mass_layers;
+      delta_mass = fabs(new_mass - prior_mass);
+      if (c.st) break;  // the reference raised inside theta_from_h
+      if (fabs(psi_cm - psi_prev) < 1e-15 && factor < 1e-13) break;
+      if (fabs(delta_mass - delta_mass_prev) < 1e-15) count_no_mass_change++;
+      else count_no_mass_change = 0;
+      if (count_no_mass_change == 5) break;
+      if (psi_cm <= 0.0 && psi_prev < 1e-50) break;
+      delta_mass_prev = delta_mass;
+    }
+    return theta;
+  }
+
+  // ---- Layer.check_column_mass (Layer.py:655-701)
+  __device__ void check_column_mass(int fd, double old_mass, double percolation, double aet, Ctx& c) {
+    const double theta_e_k1 = soil[lay(fd)].the;
+    const double mass_timestep = (old_mass + percolation) - (aet + 0.0);
+    if (fabs(f(F_THETA, fd) - theta_e_k1) < 1e-12) {
+      double current_mass = mass_balance();
+      double err = fabs(current_mass - mass_timestep);
+      bool switched = false;
+      double factor = 1.0;
+      double depth_new = f(F_DEPTH, fd);
+      long long it = 0;
+      while (fabs(err - 1e-12) > 1e-12) {
+        if (++it > c.iter_cap) {
+          raise(c, LGAR_ST_ITER_CAP);
+          break;
+        }
+        c.cnt[C_COLMASS]++;
+        if (current_mass < mass_timestep) {
+          depth_new = depth_new + 0.01 * factor;
+          switched = false;
+        } else {
+          if (!switched) {
+            switched = true;
+            factor = factor * 0.001;
+          }
+          depth_new = depth_new - (0.01 * factor);
+        }
+        f(F_DEPTH, fd) = depth_new;
+        current_mass = mass_balance();
+        err = fabs(current_mass - mass_timestep);
+      }
+    }
+  }
+
+  // ---- Layer.move_wetting_fronts (Layer.py:1254-1307): sweep from the deepest front to the top.
+  //      previous_state[i] of the reference equals the state at entry of this sweep (nothing
+  //      modifies fronts between copy_states() and here), and only the OLD theta/psi of the
+  //      front below (previous_next_front) and the front's own old values are read, so the
+  //      snapshot is carried in two registers instead of a copy of the list.
+  __device__ void move_wetting_fronts(int fd, double infiltration, double aet, double old_mass, double dt, Ctx& c) {
+    const int num_wf = n;
+    double old_theta_below = 0.0, old_psi_below = 0.0;  // previous_state of front i+1
+    int l = L - 1;
+    int o = n - cnt(L - 1);  // flat offset of list l
+    for (int i = n - 1; i >= 0; i--) {
+      while (i < o) {  // step to the list above
+        l--;
+        o -= cnt(l);
+      }
+      const int last = o + cnt(l) - 1;  // wetting_fronts[-1] of this list
+      const double old_depth = f(F_DEPTH, i), old_theta = f(F_THETA, i), old_psi = f(F_PSI, i);
+      const Soil& s = soil[l];
+      if (i < num_wf - 1) {
+        if (is_equal(i, last)) {
+          // deepest_layer_front (Layer.py:389-418): next_front = first front of the layer below
+          // (i == last), or wetting_fronts[i+1] when a non-last front is value-equal to the last
+          if (!(i < last || l < L - 1)) raise(c, LGAR_ST_NULL_NEIGHBOUR);
+          const double psi_next = f(F_PSI, i + 1);
+          f(F_THETA, i) = theta_from_h(psi_next, s, c);
+          f(F_PSI, i) = psi_next;
+        } else {
+          // wetting_front_in_layer (Layer.py:420-547); here i < last so next is in the same list
+          const double dzdt = f(F_DZDT, i);
+          if (l == 0) {
+            double prior_mass = old_depth * (old_theta - old_theta_below);
+            if (is_equal(fd, i)) prior_mass = prior_mass + (infiltration - (0.0 + aet));
+            double depth = old_depth + (dzdt * dt);
+            depth = tmin(depth, cum[L - 1]);
+            f(F_DEPTH, i) = depth;
+            const bool zero_dzdt = fabs(dzdt) <= 1e-8;  // isclose(dzdt, 0, rtol=1e-8) (Q2)
+            if (!(zero_dzdt && !tb(i))) {
+              double potential_theta = (prior_mass / depth) + f(F_THETA, i + 1);
+              f(F_THETA, i) = tmin(s.the, potential_theta);
+            }
+          } else {
+            const double plt = cum[l - 1];
+            const double depth = old_depth + (dzdt * dt);
+            f(F_DEPTH, i) = depth;
+            const double psi_old = old_psi, psi_below_old = old_psi_below;
+            const double psi_cm = old_psi, psi_below = f(F_PSI, i + 1);
+            double prior_mass = (old_depth - plt) * (old_theta - old_theta_below);
+            double new_mass = (depth - plt) * (old_theta - f(F_THETA, i + 1));
+            double dth[MAXL], dtk[MAXL];
+            for (int k = 0; k < l; k++) {  // compute_wetting_front_mass (Layer.py:561-644)
+              const Soil& sk = soil[k];
+              double theta_old = theta_from_h(psi_old, sk, c);
+              double theta_below_old = theta_from_h(psi_below_old, sk, c);
+              double local_delta_old = theta_old - theta_below_old;
+              double layer_thickness = cum[k] - 0.0;  // sic (Q5): cumulative thickness
+              prior_mass = prior_mass + (layer_thickness * local_delta_old);
+              double theta = theta_from_h(psi_cm, sk, c);
+              double theta_below = theta_from_h(psi_below, sk, c);
+              new_mass = new_mass + (layer_thickness * (theta - theta_below));
+              dth[k] = theta_below;
+              dtk[k] = layer_thickness;
+            }
+            dth[l] = f(F_THETA, i + 1);
+            dtk[l] = depth - plt;
+            if (is_equal(fd, i)) prior_mass = prior_mass + infiltration - (0.0 + aet);
+            double theta_new = theta_mass_balance(l, l, psi_cm, new_mass, prior_mass, dth, dtk, c);
+            f(F_THETA, i) = tmin(theta_new, s.the);
+          }
+          double se = se_from_theta(f(F_THETA, i), s, c);
+          f(F_PSI, i) = h_from_se(se, s, c);
+        }
+      }
+      if (num_wf == L && l == L - 1) {
+        // base_case (Layer.py:320-387) + populate_delta_thickness (:177-209)
+        const double depth = f(F_DEPTH, i) + f(F_DZDT, i) * dt;
+        f(F_DEPTH, i) = depth;
+        const double psi_old = old_psi, psi_cm = f(F_PSI, i);
+        const double base = (l > 0) ? cum[l - 1] : 0.0;
+        double prior_mass = (old_depth - base) * (old_theta - 0.0);
+        double new_mass = (depth - base) * (f(F_THETA, i) - 0.0);
+        double dth[MAXL], dtk[MAXL];
+        if (L < 2) raise(c, LGAR_ST_NULL_NEIGHBOUR);
+        for (int k = 0; k < L - 1; k++) {
+          const Soil& sk = soil[k];
+          double theta_old = theta_from_h(psi_old, sk, c);
+          prior_mass = prior_mass + thick[k] * (theta_old - 0.0);
+          double theta = theta_from_h(psi_cm, sk, c);
+          new_mass = new_mass + thick[k] * (theta - 0.0);
+          dth[k] = 0.0;
+          dtk[k] = thick[k];
+        }
+        dth[l] = 0.0;
+        dtk[l] = depth - base;
+        if (lay(fd) == l) prior_mass = prior_mass + infiltration - (0.0 + aet);
+        double theta_new = theta_mass_balance(l, L - 1, psi_cm, new_mass, prior_mass, dth, dtk, c);
+        f(F_THETA, i) = tmin(theta_new, s.the);
+        double se = se_from_theta(f(F_THETA, i), s, c);
+        f(F_PSI, i) = h_from_se(se, s, c);
+      }
+      if (i == 0) check_column_mass(fd, old_mass, infiltration, aet, c);
+      old_theta_below = old_theta;
+      old_psi_below = old_psi;
+    }
+  }
+
+  // next_to_next of get_extended_neighbors (Layer.py:733-758) for list l, list index j
+  // (flat index o + j).  Returns -1 for None, -2 if the reference would raise AttributeError.
+  __device__ int next_to_next(int l, int o, int j) {
+    const int nf = cnt(l);
+    const int i = o + j;
+    if (j < nf - 2) return i + 2;
+    const bool has_next = (j < nf - 1) || (l < L - 1);
+    if (!has_next) return -1;
+    const int nx = i + 1;
+    if (lay(nx) != lay(i)) {
+      if (l >= L - 1) return -2;  // self.next_layer is None
+      const int o1 = o + nf;      // first front of list l+1
+      if (cnt(l + 1) > 1) return o1 + 1;
+      if (l + 1 < L - 1) return o1 + cnt(l + 1);
+      return -1;
+    }
+    if (l < L - 1) return o + nf;
+    return -1;
+  }
+
+  // ---- Layer.merge_wetting_fronts (Layer.py:838-892): at most one merge per layer list per call
+  __device__ void merge_wetting_fronts(Ctx& c) {
+    int o = 0;
+    for (int l = 0; l < L; l++) {
+      const int lf = len_layers(l);
+      for (int j = 0; j < lf; j++) {
+        const int i = o + j, nx = i + 1;
+        const bool passing = (f(F_DEPTH, i) > f(F_DEPTH, nx)) && (lay(i) == lay(nx)) && !tb(nx);
+        if (passing) {
+          const int n2 = next_to_next(l, o, j);
+          if (n2 < 0) {
+            raise(c, LGAR_ST_NULL_NEIGHBOUR);  // Q10
+            break;
+          }
+          const Soil& s = soil[l];
+          const double th_c = f(F_THETA, i), th_n = f(F_THETA, nx), th_2 = f(F_THETA, n2);
+          double mass = f(F_DEPTH, i) * (th_c - th_n) + f(F_DEPTH, nx) * (th_n - th_2);
+          f(F_DEPTH, i) = mass / (th_c - th_2);
+          double se = se_from_theta(th_c, s, c);
+          f(F_PSI, i) = h_from_se(se, s, c);
+          f(F_K, i) = k_from_se(se, s.ksat, s.m, s.inv_m, c);
+          // delete_front (:888-892): pop the first front of THIS list that is value-equal to next
+          const int nf = cnt(l);
+          for (int q = 0; q < nf; q++) {
+            if (is_equal(o + q, nx)) {
+              erase_at(o + q, l);
+              break;
+            }
+          }
+          break;
+        }
+      }
+      o += cnt(l);
+    }
+  }
+
+  // ---- Layer.wetting_fronts_cross_layer_boundary (Layer.py:894-1008) + check_wetting_front
+  __device__ void cross_layer_boundary(Ctx& c) {
+    int o = 0;
+    for (int l = 0; l < L; l++) {
+      const int lf = len_layers(l);
+      const Soil& s = soil[l];
+      for (int j = 0; j < lf; j++) {
+        const int i = o + j, nx = i + 1;
+        const bool deeper = f(F_DEPTH, i) > cum[l];
+        const bool next_at_boundary = f(F_DEPTH, nx) == cum[l];
+        if (deeper && next_at_boundary) {
+          const double overshot = f(F_DEPTH, i) - f(F_DEPTH, nx);
+          double se = se_from_theta(f(F_THETA, i), s, c);
+          const double psi_c = h_from_se(se, s, c);
+          f(F_PSI, i) = psi_c;
+          f(F_K, i) = k_from_se(se, s.ksat, s.m, s.inv_m, c);
+          if (l >= L - 1) {  // recalibrate dereferences self.next_layer (None): Q9
+            raise(c, LGAR_ST_BOTTOM_REACHED);
+            return;
+          }
+          const int n2 = next_to_next(l, o, j);
+          double theta_new = theta_from_h(psi_c, soil[l + 1], c);
+          double mbal = overshot * (f(F_THETA, i) - f(F_THETA, nx));
+          if (n2 < 0) {
+            raise(c, LGAR_ST_NULL_NEIGHBOUR);
+            return;
+          }
+          double mbal_z = mbal / (theta_new - f(F_THETA, n2));
+          double depth_new = cum[l] + mbal_z;
+          f(F_DEPTH, i) = cum[l];
+          f(F_THETA, nx) = theta_new;
+          f(F_PSI, nx) = psi_c;
+          f(F_DEPTH, nx) = depth_new;
+          f(F_DZDT, nx) = f(F_DZDT, i);
+          f(F_DZDT, i) = 0.0;
+          set_flag(nx, l + 1, false);
+          set_flag(i, lay(i), true);
+        }
+      }
+      o += cnt(l);
+    }
+    // update_wetting_fronts / check_wetting_front (:939-963): fronts whose layer_num attribute
+    // exceeds their list's layer move to the head of the next list
+    o = 0;
+    for (int l = 0; l < L; l++) {
+      bool again = true;
+      while (again) {
+        again = false;
+        const int nf = cnt(l);
+        for (int j = 0; j < nf; j++) {
+          if (lay(o + j) > l) {
+            if (l >= L - 1) {
+              raise(c, LGAR_ST_NULL_NEIGHBOUR);
+              return;
+            }
+            // pop(j) from list l and insert at the head of list l+1: rotate [o+j, o+nf)
+            const int from = o + j, to = o + nf - 1;
+            if (from != to) {
+              double t5[5];
+#pragma unroll
+              for (int k = 0; k < 5; k++) t5[k] = f(k, from);
+              uint8_t tg = gb[from * NT];
+              for (int q = from; q < to; q++) copy_front(q, q + 1);
+#pragma unroll
+              for (int k = 0; k < 5; k++) f(k, to) = t5[k];
+              gb[to * NT] = tg;
+            }
+            add_cnt(l, -1);
+            add_cnt(l + 1, 1);
+            again = true;
+            break;
+          }
+        }
+      }
+      o += cnt(l);
+    }
+  }
+
+  // ---- Layer.wetting_front_cross_domain_boundary (Layer.py:1010-1053).  Unreachable in any
+  //      reference run that completes (Q9); if its condition ever holds the column is flagged.
+  __device__ double cross_domain_boundary(Ctx& c) {
+    int o = 0;
+    for (int l = 0; l < L; l++) {
+      const int lf = len_layers(l);
+      for (int j = 0; j < lf; j++) {
+        const int n2 = next_to_next(l, o, j);
+        if (n2 == -2) {
+          raise(c, LGAR_ST_NULL_NEIGHBOUR);
+          return 0.0;
+        }
+        if (n2 == -1 && f(F_DEPTH, o + j) > cum[l]) {
+          raise(c, LGAR_ST_BOTTOM_REACHED);
+          return 0.0;
+        }
+      }
+      o += cnt(l);
+    }
+    return 0.0;
+  }
+
+  // ---- Layer.fix_dry_over_wet_fronts (Layer.py:1055-1143): one fix per layer list per call
+  __device__ double fix_dry_over_wet(Ctx& c) {
+    double mc[MAXL];
+    int o = 0;
+    for (int l = 0; l < L; l++) {
+      mc[l] = 0.0;
+      const int nf = cnt(l);
+      for (int j = 0; j < nf; j++) {
+        const int i = o + j;
+        const bool has_next = (j < nf - 1) || (l < L - 1);
+        if (!has_next) continue;
+        const int nx = i + 1;
+        if (f(F_THETA, i) <= f(F_THETA, nx) && lay(i) == lay(nx)) {
+          const double mass_before = mass_balance();
+          const int popped_layer = lay(i);
+          erase_at(i, l);  // the former next front now sits at flat index i
+          if (popped_layer > 0) cleanup_wetting_fronts(i, c);
+          const double mass_after = mass_balance();
+          mc[l] = mc[l] + fabs(mass_after - mass_before);
+          break;
+        }
+      }
+      o += cnt(l);
+    }
+    double tot = mc[L - 1];
+    for (int l = L - 2; l >= 0; l--) tot = mc[l] + tot;
+    return tot;
+  }
+  // cleanup_wetting_fronts (:1098-1115): the search is by VALUE from the top of the column
+  __device__ void cleanup_wetting_fronts(int nx, Ctx& c) {
+    int o = 0;
+    for (int l = 0; l < L; l++) {
+      const int nf = cnt(l);
+      for (int j = 0; j < nf; j++) {
+        const int i = o + j;
+        if (is_equal(i, nx)) {
+          const Soil& s = soil[l];
+          double se_k = se_from_theta(f(F_THETA, i), s, c);
+          f(F_PSI, i) = h_from_se(se_k, s, c);
+          // update_layer_fronts (:1117-1143, Q15): every front of every list above dry.layer_num
+          const int dry_layer = lay(i);
+          const double dry_theta = f(F_THETA, i), dry_psi = f(F_PSI, i);
+          int o2 = 0;
+          for (int l2 = 0; l2 < L && l2 < dry_layer; l2++) {
+            const Soil& s2 = soil[l2];
+            const int nf2 = cnt(l2);
+            for (int q = 0; q < nf2; q++) {
+              double se_l = se_from_theta(dry_theta, s2, c);
+              f(F_PSI, o2 + q) = h_from_se(se_l, s2, c);
+              f(F_THETA, o2 + q) = theta_from_h(dry_psi, s2, c);
+            }
+            o2 += nf2;
+          }
+          return;
+        }
+      }
+      o += nf;
+    }
+    raise(c, LGAR_ST_INDEX_ERROR);
+  }
+
+  // ---- Layer.update_psi (Layer.py:1157-1174)
+  __device__ void update_psi(Ctx& c) {
+    int o = 0;
+    for (int l = 0; l < L; l++) {
+      const int lf = len_layers(l);
+      const Soil& s = soil[l];
+      for (int j = 0; j < lf; j++) {
+        double se = se_from_theta(f(F_THETA, o + j), s, c);
+        f(F_PSI, o + j) = h_from_se(se, s, c);
+        f(F_K, o + j) = k_from_se(se, s.ksat, s.m, s.inv_m, c);
+      }
+      o += cnt(l);
+    }
+  }
+
+  // ---- Layer.calc_bottom_sum (Layer.py:1557-1582) from list l0 upward in index
+  __device__ double calc_bottom_sum(int l0, double bottom_sum, double psi, int front_layer, Ctx& c) {
+    for (int k = l0;; k++) {
+      const Soil& sk = soil[k];
+      double theta_prev = theta_from_h(psi, sk, c);
+      double se_prev = se_from_theta(theta_prev, sk, c);
+      double kk = k_from_se(se_prev, sk.ksat, sk.m, sk.inv_m, c);
+      double plt = (k != 0) ? cum[k - 1] : 0.0;
+      bottom_sum = bottom_sum + ((cum[k] - plt) / kk);
+      if (k + 1 >= L) {
+        raise(c, LGAR_ST_NULL_NEIGHBOUR);
+        return bottom_sum;
+      }
+      if (k + 1 == front_layer) return bottom_sum;
+    }
+  }
+
+  // ---- dpLGAR.move_wetting_front (models/dpLGAR.py:340-367); returns the bottom flux
+  __device__ double move_wetting_front(int fd, double infiltration, double& AET_sub, double old_mass, double dt,
+                                       Ctx& c) {
+    move_wetting_fronts(fd, infiltration, AET_sub, old_mass, dt, c);
+    merge_wetting_fronts(c);
+    cross_layer_boundary(c);
+    merge_wetting_fronts(c);
+    double bottom_flux = 0.0 + cross_domain_boundary(c);
+    double mass_change = fix_dry_over_wet(c);
+    if (fabs(mass_change) > 1e-7) AET_sub = AET_sub - mass_change;
+    update_psi(c);
+    return bottom_flux;
+  }
+};
+
+}  // namespace lgar

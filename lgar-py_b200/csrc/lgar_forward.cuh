@@ -1,0 +1,544 @@
+// =====================================================================================
+// lgar_forward.cuh -- persistent forward kernel: all columns x all forcing steps in ONE launch.
+//
+// Scheduling.  Work item = (tile of 32 columns, chunk of `chunk_steps` forcing steps).  Items
+// are handed out chunk-major from one atomic counter to the resident warps (grid = SMs x CTAs
+// per SM); item (tile, c) needs item (tile, c-1), which was handed out `ntiles` items earlier
+// and is therefore finished or running on a resident warp -- a short acquire-spin on
+// done[tile] resolves it without any possibility of deadlock.  Between chunks the column state
+// (<= 16 fronts x 5 doubles + a few scalars) round-trips through global memory (L2): this
+// removes the tail of a static column->warp assignment, balances slow and fast columns, and
+// the chunk-start states double as the checkpoints of the reverse-mode kernel.
+//
+// One sub-step follows models/dpLGAR.py:154-299 exactly; the three places that evaluate Geff
+// (insert_water, calc_dry_depth, calc_dzdt) are warp-convergent call sites of geff_warp().
+// =====================================================================================
+#pragma once
+#include "lgar_device.cuh"
+
+namespace lgar {
+
+// slots of the per-column state record (doubles), after the 5*FM front fields
+enum StateSlot {
+  S_PONDED = 0, S_PREV_PRECIP = 1, S_END_VOL = 2, S_GIUH = 3, /* 8 */ S_SUMS = 11, /* NOUT */ S_COUNT = 11 + NOUT
+};
+// int state: n, cntpk, status, crash_step
+constexpr int NI_STATE = 4;
+
+template <int FM>
+__host__ __device__ constexpr int state_doubles() { return 5 * FM + S_COUNT; }
+
+struct KParams {
+  lgar_problem p;
+  lgar_outputs o;
+  // workspace
+  double* state_d;       // [nckpt][state_doubles][Bp]
+  int32_t* state_i;      // [nckpt][NI_STATE][Bp]
+  uint8_t* state_f;      // [nckpt][FM][Bp]
+  int32_t* done;         // [ntiles] chunks completed per tile
+  unsigned long long* next_item;
+  int32_t Bp;            // B rounded up to a multiple of 32
+  int32_t ntiles, nchunks, chunk_steps;
+  int32_t keep_ckpt;     // 1: state of chunk c is stored at index c (+ final at nchunks)
+  long long iter_cap;
+};
+
+template <int FM>
+struct Tile {
+  Column<FM> col;
+  Ctx ctx;
+  double acc[NOUT];   // per-forcing-step accumulators (reset every step)
+  double sums[NOUT];  // running sums over time
+  int crash_step;
+  int psiwp_st;       // guard raised while precomputing psi_wp (reported on first AET use)
+};
+
+// ---- Layer.calc_aet (Layer.py:760-783) -> calc_aet (lgar/aet.py:17-51)
+template <int FM>
+__device__ __forceinline__ void precompute_psi_wp(Tile<FM>& T, double wilting_psi) {
+  Ctx cc = T.ctx;
+  cc.st = 0;
+  const Soil& s = T.col.soil[0];
+  double theta_fc = (s.the - s.thr) * 0.75 + s.thr;  // GlobalParams.py:75
+  double wp_head_theta = theta_from_h(wilting_psi, s, cc);
+  double theta_wp = (theta_fc - wp_head_theta) * 0.5 + wp_head_theta;
+  double se = se_from_theta(theta_wp, s, cc);
+  T.col.psi_wp = h_from_se(se, s, cc);
+  T.psiwp_st = cc.st;
+}
+template <int FM>
+__device__ __forceinline__ double calc_aet(Tile<FM>& T, double pet, double dt) {
+  Ctx& c = T.ctx;
+  if (T.psiwp_st) raise(c, T.psiwp_st);
+  c.cnt[C_THETA_H] += 1;
+  c.cnt[C_H_SE] += 1;
+  double h_ratio = 1.0 + safe_pow(T.col.f(F_PSI, 0) / T.col.psi_wp, 3.0, c);
+  double aet_ = pet * (1.0 / h_ratio) * dt;
+  double r = (aet_ < 0.0) ? 0.0 : aet_;  // torch.clamp(min=0, max=pet): upper clamp is the RATE (sic)
+  r = (r > pet) ? pet : r;
+  return r;
+}
+
+// set_internal_states (models/dpLGAR.py:97-147), Layer.__init__ (Layer.py:22-90),
+// WettingFront.__init__ (WettingFront.py:18-49), generate_soil_metrics (data/utils.py:40-105)
+template <int FM>
+__device__ void init_column(Tile<FM>& T, double initial_psi) {
+  Column<FM>& C = T.col;
+  Ctx& c = T.ctx;
+  C.n = 0;
+  C.cntpk = 0;
+  for (int l = 0; l < C.L; l++) {
+    const Soil& s = C.soil[l];
+    double theta_init = theta_from_h(initial_psi, s, c);
+    const int i = C.n;
+    C.f(F_DEPTH, i) = C.cum[l];
+    C.f(F_THETA, i) = theta_init;
+    C.f(F_DZDT, i) = 0.0;
+    double se = se_from_theta(theta_init, s, c);
+    C.f(F_PSI, i) = initial_psi;
+    C.f(F_K, i) = k_from_se(se, s.ksat, s.m, s.inv_m, c);
+    C.set_flag(i, l, true);
+    C.n++;
+    C.add_cnt(l, 1);
+  }
+  C.ending_volume = C.mass_balance();
+  C.ponded_water = 0.0;
+  C.previous_precip = 0.0;
+  for (int i = 0; i < NGIUH; i++) C.giuh[i] = 0.0;
+  for (int k = 0; k < NOUT; k++) T.sums[k] = 0.0;
+}
+
+// ---- one sub-step: models/dpLGAR.py:176-298.  Warp-convergent: every lane of the warp calls it;
+//      lanes with act == false only take part in the cooperative Geff evaluations.
+template <int FM>
+__device__ void substep(Tile<FM>& T, bool act, double precip_rate, double pet_rate, const KParams& K,
+                        double* nodebuf) {
+  Column<FM>& C = T.col;
+  Ctx& c = T.ctx;
+  const double dt = K.p.subcycle_length_h;
+  const int nint = K.p.nint;
+  const int L = C.L;
+  act = act && (c.st == 0);
+
+  double precip_sub = 0.0, ponded_depth_sub = 0.0, ponded_water_sub = 0.0, percolation_sub = 0.0;
+  double runoff_sub = 0.0, infiltration_sub = 0.0, AET_sub = 0.0;
+  double ending_volume_sub = C.ending_volume;
+  bool create = false, saturated = false;
+  int fd = 0;
+  if (act) {
+    c.cnt[C_SUB]++;
+    precip_sub = precip_rate * dt;
+    const double pet_sub = pet_rate * dt;
+    ponded_depth_sub = precip_sub + C.ponded_water;
+    create = (C.previous_precip == 0.0) && (precip_sub > 0.0) && (C.ponded_water == 0.0);  // :310-323
+    fd = C.free_drainage_front();
+    saturated = C.f(F_THETA, 0) >= C.soil[0].the;  // Layer.is_saturated (:785-793)
+    if (pet_rate > 0.0) AET_sub = calc_aet(T, pet_rate, dt);
+    T.acc[LGAR_OUT_PRECIP] = T.acc[LGAR_OUT_PRECIP] + precip_sub;
+    T.acc[LGAR_OUT_PET] = T.acc[LGAR_OUT_PET] + fmax(pet_sub, 0.0);
+  }
+  const bool brA = act && create && !saturated;             // create a surficial front
+  const bool brB = act && !create && (ponded_depth_sub > 0.0);  // insert water
+
+  // ---- phase 1: Layer.insert_water (Layer.py:1418-1536) for branch-B lanes
+  {
+    int lfp = 0, nx_fd = 0;
+    bool needG = false;
+    double theta_1 = 0.0, theta_2 = 0.0;
+    if (brB) {
+      lfp = C.lay(fd);
+      const int o = C.off(lfp);
+      // get_drainage_neighbors (:1584-1607, Q6): the front after the FIRST front of fd's layer list
+      if (C.cnt(lfp) > 1 || lfp < L - 1) nx_fd = o + 1;
+      else raise(c, LGAR_ST_NULL_NEIGHBOUR);
+      if (c.st == 0 && C.n != L) {
+        needG = true;
+        theta_1 = C.f(F_THETA, nx_fd);
+        theta_2 = C.soil[lfp].the;
+      }
+    }
+    const double geff = geff_warp(needG, theta_1, theta_2, C.soil[needG ? lfp : 0], nint, nodebuf, c);
+    if (brB && c.st == 0) {
+      const double h_p_ = (ponded_depth_sub - precip_sub) * dt;
+      const double h_p = (h_p_ < 0.0) ? 0.0 : h_p_;  // clamp(min=0)
+      const double fd_depth = C.f(F_DEPTH, fd);
+      double f_p = 0.0;
+      if (lfp == 0) {
+        f_p = C.soil[0].ksat * (1.0 + (geff + h_p) / fd_depth);
+      } else if (C.n == L) {
+        raise(c, LGAR_ST_NULL_NEIGHBOUR);  // `free_drainage_ksat` unbound in the reference
+      } else {
+        const double fd_ksat = C.soil[lfp].ksat * K.p.frozen_factor;
+        double bottom_sum = (fd_depth - C.cum[lfp - 1]) / fd_ksat;
+        // calc_bottom_sum_f_p (:1538-1555, Q18): saturated K for layer 0, then the
+        // unsaturated calc_bottom_sum for the remaining upper layers
+        const double k0 = C.soil[0].ksat * K.p.frozen_factor;
+        bottom_sum = bottom_sum + ((C.cum[0] - 0.0) / k0);
+        if (1 != lfp) bottom_sum = C.calc_bottom_sum(1, bottom_sum, C.f(F_PSI, fd), lfp, c);
+        f_p = (fd_depth / bottom_sum) + ((geff + h_p) * fd_ksat / fd_depth);
+      }
+      const double pt_ = ponded_depth_sub - f_p * dt - 0.0;
+      const double ponded_temp = (pt_ < 0.0) ? 0.0 : pt_;
+      const double fp_cm = f_p * dt + 0.0 / dt;
+      if (C.pdm > 0.0) {
+        if (ponded_temp < C.pdm) {
+          infiltration_sub = tmin(ponded_depth_sub, fp_cm);
+          ponded_depth_sub = ponded_depth_sub - infiltration_sub;
+        } else if (ponded_temp > C.pdm) {
+          ponded_depth_sub = C.pdm;
+          infiltration_sub = fp_cm;
+        }
+        const double r_ = ponded_temp - C.pdm;
+        runoff_sub = (r_ < 0.0) ? 0.0 : r_;
+      } else {
+        infiltration_sub = tmin(ponded_depth_sub, fp_cm);
+        const double r_ = ponded_depth_sub - infiltration_sub;
+        ponded_depth_sub = C.pdm;
+        runoff_sub = (r_ < 0.0) ? 0.0 : r_;
+      }
+      T.acc[LGAR_OUT_INFILTRATION] = T.acc[LGAR_OUT_INFILTRATION] + infiltration_sub;
+      T.acc[LGAR_OUT_RUNOFF] = T.acc[LGAR_OUT_RUNOFF] + runoff_sub;
+      percolation_sub = infiltration_sub;
+      ponded_water_sub = ponded_depth_sub;
+    }
+  }
+
+  // ---- phase 2: move the fronts (branch A moves without adding water; every non-create lane moves
+  //      with its infiltration).  models/dpLGAR.py:206-212 and :249-266
+  if (act && c.st == 0 && (brA || !create)) {
+    const double infil_arg = create ? 0.0 : infiltration_sub;
+    const double bottom = C.move_wetting_front(fd, infil_arg, AET_sub, ending_volume_sub, dt, c);
+    if (!create) {
+      percolation_sub = bottom;
+      T.acc[LGAR_OUT_PERCOLATION] = T.acc[LGAR_OUT_PERCOLATION] + percolation_sub;
+    }  // branch A drops the bottom flux (Q7)
+  }
+
+  // ---- phase 3: calc_dry_depth (Layer.py:1309-1334) + create_surficial_front (:1336-1416)
+  {
+    const bool needG = brA && c.st == 0;
+    double theta_1 = 0.0, theta_2 = 0.0;
+    if (needG) {
+      theta_1 = C.f(F_THETA, 0);
+      theta_2 = C.soil[0].the;
+    }
+    const double geff = geff_warp(needG, theta_1, theta_2, C.soil[0], nint, nodebuf, c);
+    if (needG && c.st == 0) {
+      const Soil& s = C.soil[0];
+      const double cur_theta = C.f(F_THETA, 0);
+      const double delta_theta = s.the - cur_theta;
+      const double tau = dt * s.ksat / delta_theta;
+      double dry_depth = 0.5 * (tau + sqrt(tau * tau + 4.0 * tau * geff));
+      dry_depth = tmin(C.cum[0], dry_depth);
+      double theta_new;
+      bool to_bottom;
+      if (dry_depth * delta_theta > ponded_depth_sub) {
+        infiltration_sub = ponded_depth_sub;
+        theta_new = tmin(cur_theta + ponded_depth_sub / dry_depth, s.the);
+        to_bottom = false;
+        ponded_depth_sub = 0.0;
+      } else {
+        infiltration_sub = dry_depth * delta_theta;
+        ponded_depth_sub = ponded_depth_sub - (dry_depth * delta_theta);
+        theta_new = s.the;
+        to_bottom = !(dry_depth < C.cum[0]);
+      }
+      if (C.insert_at(0, 0, c)) {
+        C.f(F_DEPTH, 0) = dry_depth;
+        C.f(F_THETA, 0) = theta_new;
+        C.set_flag(0, 0, to_bottom);
+        double se = se_from_theta(theta_new, s, c);
+        C.f(F_PSI, 0) = h_from_se(se, s, c);
+        C.f(F_K, 0) = k_from_se(se, s.ksat, s.m, s.inv_m, c) * K.p.frozen_factor;
+        C.f(F_DZDT, 0) = 0.0;
+      }
+      T.acc[LGAR_OUT_INFILTRATION] = T.acc[LGAR_OUT_INFILTRATION] + infiltration_sub;
+    }
+  }
+  // update_ponded_depth (models/dpLGAR.py:369-382) for every lane that did not insert water
+  if (act && !brB) {
+    if (ponded_depth_sub < C.pdm) {
+      runoff_sub = 0.0;
+      ponded_water_sub = ponded_depth_sub;
+      ponded_depth_sub = 0.0;
+    } else {
+      runoff_sub = ponded_depth_sub - C.pdm;
+      ponded_depth_sub = C.pdm;
+      ponded_water_sub = ponded_depth_sub;
+    }
+    T.acc[LGAR_OUT_RUNOFF] = T.acc[LGAR_OUT_RUNOFF] + runoff_sub;
+  }
+
+  // ---- phase 4: Layer.calc_dzdt (Layer.py:1176-1252), one cooperative Geff per moving front
+  {
+    const bool go = act && c.st == 0;
+    const int my_n = go ? C.n - 1 : 0;  // the deepest front of the domain is excluded
+    int nmax = my_n;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, d));
+    int l = 0, o_next = go ? C.cnt(0) : 0;  // list layer of flat index i
+    for (int i = 0; i < nmax; i++) {
+      bool needG = false;
+      double theta_1 = 0.0, theta_2 = 0.0, bottom_sum = 0.0;
+      const bool mine = go && (i < my_n) && (c.st == 0);
+      if (mine) {
+        while (i >= o_next) {
+          l++;
+          o_next += C.cnt(l);
+        }
+        theta_1 = C.f(F_THETA, i + 1);
+        theta_2 = C.f(F_THETA, i);
+        if (C.tb(i)) {
+          C.f(F_DZDT, i) = 0.0;
+        } else {
+          if (C.lay(i) > 0) {
+            if (l == 0) raise(c, LGAR_ST_NULL_NEIGHBOUR);  // self.previous_layer is None
+            else bottom_sum = 0.0 + (C.f(F_DEPTH, i) - C.cum[l - 1]) / C.f(F_K, i);
+          } else if (theta_1 > theta_2) {
+            raise(c, LGAR_ST_THETA_ORDER);
+          }
+          needG = (c.st == 0);
+        }
+      }
+      const double geff = geff_warp(needG, theta_1, theta_2, C.soil[needG ? l : 0], nint, nodebuf, c);
+      if (needG && c.st == 0) {
+        const Soil& s = C.soil[l];
+        const double depth = C.f(F_DEPTH, i);
+        const double delta_theta = theta_2 - theta_1;
+        double dzdt = 0.0;
+        if (C.lay(i) == 0) {
+          if (delta_theta > 0.0)
+            dzdt = 1.0 / delta_theta * (s.ksat * (geff + ponded_depth_sub) / depth + C.f(F_K, i));
+        } else {
+          const double denominator = C.calc_bottom_sum(0, bottom_sum, C.f(F_PSI, i), C.lay(i), c);
+          if (delta_theta > 0.0)
+            dzdt = (1.0 / delta_theta) * ((depth / denominator) + s.ksat * (geff + ponded_depth_sub) / depth);
+        }
+        C.f(F_DZDT, i) = dzdt;
+      }
+    }
+  }
+
+  if (act) {
+    ending_volume_sub = C.mass_balance();
+    C.previous_precip = precip_sub;
+    C.ending_volume = ending_volume_sub;
+    T.acc[LGAR_OUT_AET] = T.acc[LGAR_OUT_AET] + AET_sub;
+    C.ponded_water = ponded_water_sub;
+    // GIUH (lgar/giuh.py:8-20, models/dpLGAR.py:292-298)
+    const int ng = K.p.num_giuh;
+    double qsum = 0.0;
+    for (int i = 0; i < ng; i++) qsum = qsum + C.giuh[i];
+    if (qsum > 0.0 || runoff_sub > 0.0) {
+      for (int i = 0; i < ng; i++) C.giuh[i] = C.giuh[i] + (K.p.giuh_ordinates[i] * runoff_sub);
+      const double now = C.giuh[0];
+      for (int i = 0; i + 1 < ng; i++) C.giuh[i] = C.giuh[i + 1];
+      C.giuh[ng - 1] = 0.0;
+      T.acc[LGAR_OUT_GIUH_RUNOFF] = T.acc[LGAR_OUT_GIUH_RUNOFF] + now;
+      T.acc[LGAR_OUT_DISCHARGE] = T.acc[LGAR_OUT_DISCHARGE] + now;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// state save / restore (global memory, column fastest).  Loads bypass L1 (__ldcg): the
+// record may have been written by a warp on another SM.
+// ------------------------------------------------------------------------------------
+template <int FM>
+__device__ void save_state(const KParams& K, int slot, int b, Tile<FM>& T) {
+  const size_t Bp = K.Bp;
+  double* sd = K.state_d + (size_t)slot * state_doubles<FM>() * Bp + b;
+  Column<FM>& C = T.col;
+  for (int i = 0; i < C.n; i++) {
+#pragma unroll
+    for (int k = 0; k < 5; k++) sd[(size_t)(k * FM + i) * Bp] = C.f(k, i);
+  }
+  double* ss = sd + (size_t)(5 * FM) * Bp;
+  ss[(size_t)S_PONDED * Bp] = C.ponded_water;
+  ss[(size_t)S_PREV_PRECIP * Bp] = C.previous_precip;
+  ss[(size_t)S_END_VOL * Bp] = C.ending_volume;
+  for (int i = 0; i < NGIUH; i++) ss[(size_t)(S_GIUH + i) * Bp] = C.giuh[i];
+  for (int k = 0; k < NOUT; k++) ss[(size_t)(S_SUMS + k) * Bp] = T.sums[k];
+  int32_t* si = K.state_i + (size_t)slot * NI_STATE * Bp + b;
+  si[0] = C.n;
+  si[Bp] = (int32_t)C.cntpk;
+  si[2 * Bp] = T.ctx.st;
+  si[3 * Bp] = T.crash_step;
+  uint8_t* sf = K.state_f + (size_t)slot * FM * Bp + b;
+  for (int i = 0; i < C.n; i++) sf[(size_t)i * Bp] = C.gb[i * NT];
+}
+template <int FM>
+__device__ void load_state(const KParams& K, int slot, int b, Tile<FM>& T) {
+  const size_t Bp = K.Bp;
+  const double* sd = K.state_d + (size_t)slot * state_doubles<FM>() * Bp + b;
+  Column<FM>& C = T.col;
+  const int32_t* si = K.state_i + (size_t)slot * NI_STATE * Bp + b;
+  C.n = __ldcg(si);
+  C.cntpk = (unsigned)__ldcg(si + Bp);
+  T.ctx.st = __ldcg(si + 2 * Bp);
+  T.crash_step = __ldcg(si + 3 * Bp);
+  for (int i = 0; i < C.n; i++) {
+#pragma unroll
+    for (int k = 0; k < 5; k++) C.f(k, i) = __ldcg(sd + (size_t)(k * FM + i) * Bp);
+  }
+  const double* ss = sd + (size_t)(5 * FM) * Bp;
+  C.ponded_water = __ldcg(ss + (size_t)S_PONDED * Bp);
+  C.previous_precip = __ldcg(ss + (size_t)S_PREV_PRECIP * Bp);
+  C.ending_volume = __ldcg(ss + (size_t)S_END_VOL * Bp);
+  for (int i = 0; i < NGIUH; i++) C.giuh[i] = __ldcg(ss + (size_t)(S_GIUH + i) * Bp);
+  for (int k = 0; k < NOUT; k++) T.sums[k] = __ldcg(ss + (size_t)(S_SUMS + k) * Bp);
+  const uint8_t* sf = K.state_f + (size_t)slot * FM * Bp + b;
+  for (int i = 0; i < C.n; i++) C.gb[i * NT] = __ldcg(sf + (size_t)i * Bp);
+}
+
+// load the column's parameters and derive the per-layer constants
+// (models/dpLGAR.py:41-57, data/utils.py:75-91 calc_m, GlobalParams.py:99-110)
+template <int FM>
+__device__ void load_params(const KParams& K, int b, Tile<FM>& T) {
+  const lgar_problem& p = K.p;
+  Column<FM>& C = T.col;
+  const size_t B = p.num_columns;
+  C.L = p.num_layers;
+  double cumv = 0.0;
+  for (int l = 0; l < C.L; l++) {
+    Soil& s = C.soil[l];
+    s.alpha = __ldg(p.alpha + l * B + b);
+    s.n = __ldg(p.n + l * B + b);
+    s.ksat = __ldg(p.ksat + l * B + b);
+    s.the = __ldg(p.theta_e + l * B + b);
+    s.thr = __ldg(p.theta_r + l * B + b);
+    s.m = 1.0 - (1.0 / s.n);
+    s.inv_m = 1.0 / s.m;
+    s.ninv_m = -1.0 / s.m;
+    s.inv_n = 1.0 / s.n;
+    const double th = __ldg(p.thickness + l * B + b);
+    C.thick[l] = th;
+    cumv = (l == 0) ? th : cumv + th;
+    C.cum[l] = cumv;
+  }
+  C.pdm = __ldg(p.ponded_depth_max + b);
+}
+
+template <int FM, bool COUNT, bool DUMP>
+__global__ void __launch_bounds__(NT) lgar_forward_kernel(const KParams K) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sm_fields = reinterpret_cast<double*>(smem_raw);                       // [5*FM][NT]
+  double* sm_nodes = sm_fields + 5 * FM * NT;                                    // [WARPS][NODEBUF]
+  uint8_t* sm_flags = reinterpret_cast<uint8_t*>(sm_nodes + WARPS * NODEBUF);    // [FM][NT]
+  __shared__ unsigned long long sm_item[WARPS];
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  double* nodebuf = sm_nodes + warp * NODEBUF;
+  const lgar_problem& p = K.p;
+  const int Tn = p.num_steps;
+  const int S = p.num_subcycles;
+  const size_t B = p.num_columns;
+  const unsigned long long nitems = (unsigned long long)K.ntiles * K.nchunks;
+
+  Tile<FM> T;
+  T.col.fb = sm_fields + threadIdx.x;
+  T.col.gb = sm_flags + threadIdx.x;
+  T.ctx.iter_cap = K.iter_cap;
+
+  for (;;) {
+    if (lane == 0) sm_item[warp] = atomicAdd(K.next_item, 1ULL);
+    __syncwarp();
+    const unsigned long long item = sm_item[warp];
+    __syncwarp();
+    if (item >= nitems) break;
+    const int chunk = (int)(item / K.ntiles);
+    const int tile = (int)(item % K.ntiles);
+    const int b = tile * 32 + lane;
+    const bool valid = (size_t)b < B;
+    const int bb = valid ? b : (int)B - 1;  // clamp for loads; results of invalid lanes are never stored
+
+    // wait for the previous chunk of this tile (acquire)
+    if (chunk > 0) {
+      if (lane == 0) {
+        volatile int32_t* d = K.done + tile;
+        while (*d < chunk) __nanosleep(200);
+      }
+      __syncwarp();
+      __threadfence();
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) T.ctx.cnt[k] = 0;
+    load_params(K, bb, T);
+    const int slot_in = K.keep_ckpt ? chunk : 0;
+    if (chunk == 0) {
+      T.ctx.st = 0;
+      T.crash_step = -1;
+      init_column(T, __ldg(p.initial_psi + bb));
+      if (T.ctx.st) T.crash_step = 0;
+      if (valid && K.o.start_volume) K.o.start_volume[b] = T.col.ending_volume;
+      if (K.keep_ckpt && valid) save_state(K, 0, b, T);
+    } else {
+      load_state(K, slot_in, bb, T);
+    }
+    precompute_psi_wp(T, p.wilting_point_psi);
+    const int site = (p.site_index && valid) ? __ldg(p.site_index + b) : 0;
+    const double* frc = p.forcing + (size_t)site * Tn * 2;
+    const int t0 = chunk * K.chunk_steps;
+    const int t1 = min(Tn, t0 + K.chunk_steps);
+
+    for (int t = t0; t < t1; t++) {
+      const double2 x = __ldg(reinterpret_cast<const double2*>(frc) + t);
+#pragma unroll
+      for (int k = 0; k < NOUT; k++) T.acc[k] = 0.0;
+      const bool alive = valid && (T.ctx.st == 0);
+      for (int sc = 0; sc < S; sc++) substep(T, alive, x.x, x.y, K, nodebuf);
+      if (alive && T.ctx.st != 0) T.crash_step = t;
+      const bool ok = valid && (T.ctx.st == 0);
+      T.acc[LGAR_OUT_ENDING_VOLUME] = T.col.ending_volume;
+      T.acc[LGAR_OUT_PONDED_WATER] = T.col.ponded_water;
+      if (valid) {
+        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+        if (K.o.per_step) {
+#pragma unroll
+          for (int k = 0; k < NOUT; k++)
+            if (K.o.per_step_mask & (1u << k))
+              K.o.per_step[((size_t)k * Tn + t) * B + b] = ok ? T.acc[k] : qnan;
+        }
+        if (ok) {
+#pragma unroll
+          for (int k = 0; k < NOUT; k++)
+            T.sums[k] = (k == LGAR_OUT_ENDING_VOLUME || k == LGAR_OUT_PONDED_WATER) ? T.acc[k] : T.sums[k] + T.acc[k];
+        }
+        if (K.o.num_fronts) K.o.num_fronts[(size_t)t * B + b] = ok ? T.col.n : 0;
+        if (DUMP && K.o.fronts) {
+          for (int i = 0; i < LGAR_MAX_FRONTS; i++) {
+            const bool has = ok && i < T.col.n;
+#pragma unroll
+            for (int k = 0; k < 5; k++)
+              K.o.fronts[(((size_t)t * LGAR_MAX_FRONTS + i) * 5 + k) * B + b] = has ? T.col.f(k, i) : 0.0;
+            if (K.o.front_layer) K.o.front_layer[((size_t)t * LGAR_MAX_FRONTS + i) * B + b] = has ? (int8_t)T.col.lay(i) : (int8_t)-1;
+            if (K.o.front_to_bottom) K.o.front_to_bottom[((size_t)t * LGAR_MAX_FRONTS + i) * B + b] = has ? (int8_t)T.col.tb(i) : (int8_t)0;
+          }
+        }
+      }
+    }
+
+    // publish the state for the next chunk of this tile (release)
+    const int slot_out = K.keep_ckpt ? chunk + 1 : 0;
+    if (valid) save_state(K, slot_out, b, T);
+    if (chunk == K.nchunks - 1 && valid) {
+      if (K.o.sums) {
+#pragma unroll
+        for (int k = 0; k < NOUT; k++) K.o.sums[(size_t)k * B + b] = T.sums[k];
+      }
+      if (K.o.status) K.o.status[b] = T.ctx.st;
+      if (K.o.crash_step) K.o.crash_step[b] = T.crash_step;
+    }
+    if (COUNT && K.o.counters && valid) {
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        if (T.ctx.cnt[k]) atomicAdd(K.o.counters + k, (unsigned long long)T.ctx.cnt[k]);
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicExch(K.done + tile, chunk + 1);
+  }
+}
+
+}  // namespace lgar
