@@ -117,9 +117,9 @@ typedef struct lgar_problem {
 
 /* Output buffers.  Any pointer may be NULL (that output is skipped).                           */
 typedef struct lgar_outputs {
-  double* per_step;        /* [NOUT][T][B]; rows selected by per_step_mask are written, the
-                              others are left untouched                                          */
-  uint32_t per_step_mask;  /* bit k = write output k                                            */
+  double* per_step;        /* [popcount(per_step_mask)][T][B]: the selected outputs, compact, in
+                              increasing output index                                            */
+  uint32_t per_step_mask;  /* bit k = store output k                                            */
   int32_t reserved0;
   double* sums;            /* [NOUT][B]: sum over t of every output (ENDING_VOLUME and
                               PONDED_WATER: value after the last step)                          */
@@ -153,7 +153,7 @@ size_t lgar_workspace_bytes(const lgar_problem* p, int with_grad);
 int lgar_forward(const lgar_problem* p, const lgar_outputs* out, void* workspace_dev,
                  size_t workspace_bytes, int keep_checkpoints, void* stream);
 
-/* Reverse mode.  grad_per_step[NOUT][T][B] (rows selected by grad_mask) and/or
+/* Reverse mode.  grad_per_step[popcount(grad_mask)][T][B] (same compact layout) and/or
  * grad_sums[NOUT][B] are dL/d(output); writes dL/d(alpha,n,ksat) as [L][B] arrays.
  * Must follow an lgar_forward with keep_checkpoints on the same workspace and problem.         */
 int lgar_backward(const lgar_problem* p, const double* grad_per_step, uint32_t grad_mask,

@@ -114,7 +114,7 @@ def output_mask(names) -> int:
 
 @dataclass
 class ForwardResult:
-    per_step: Optional[torch.Tensor]   # [NOUT,T,B]; only rows in `mask` are defined
+    per_step: Optional[torch.Tensor]   # [popcount(mask),T,B]: selected outputs in increasing index
     mask: int
     sums: torch.Tensor                 # [NOUT,B]
     start_volume: torch.Tensor         # [B]
@@ -129,7 +129,7 @@ class ForwardResult:
     def __getitem__(self, name) -> torch.Tensor:
         k = OUT_NAMES.index(name)
         assert self.per_step is not None and (self.mask >> k) & 1, f"output {name} was not requested"
-        return self.per_step[k]
+        return self.per_step[bin(self.mask & ((1 << k) - 1)).count("1")]
 
 
 def _param(x, ens: ColumnEnsemble):
@@ -156,7 +156,7 @@ def forward_raw(ens: ColumnEnsemble, alpha, n, ksat, outputs=("runoff", "percola
     mask = output_mask(outputs) if per_step else 0
     o = _capi.Outputs()
     res = ForwardResult(
-        per_step=torch.zeros((NUM_OUTPUTS, T, B), dtype=F64, device=dev) if mask else None, mask=mask,
+        per_step=torch.empty((bin(mask).count("1"), T, B), dtype=F64, device=dev) if mask else None, mask=mask,
         sums=torch.empty((NUM_OUTPUTS, B), dtype=F64, device=dev),
         start_volume=torch.empty(B, dtype=F64, device=dev),
         status=torch.empty(B, dtype=torch.int32, device=dev),
@@ -241,6 +241,6 @@ def lgar_columns(alpha, n, ksat, ens: ColumnEnsemble, outputs=("runoff", "percol
     ne = nn_ if nn_.dim() == 2 else nn_.unsqueeze(1).expand(ens.num_layers, ens.num_columns)
     ke = k if k.dim() == 2 else k.unsqueeze(1).expand(ens.num_layers, ens.num_columns)
     per_step, sums, sv, st, cs = _LGARFunction.apply(ae.contiguous(), ne.contiguous(), ke.contiguous(), ens, mask)
-    out = {name: per_step[OUT_NAMES.index(name)] for name in outputs}
+    out = {name: per_step[bin(mask & ((1 << OUT_NAMES.index(name)) - 1)).count("1")] for name in outputs}
     out.update(sums=sums, start_volume=sv, status=st, crash_step=cs)
     return out

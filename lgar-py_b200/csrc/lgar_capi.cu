@@ -201,11 +201,12 @@ int lgar_forward(const lgar_problem* p, const lgar_outputs* out, void* workspace
   if (out->counters) CUDA_TRY(cudaMemsetAsync(out->counters, 0, 8 * sizeof(unsigned long long), st));
   const bool count = out->counters != nullptr;
   const bool dump = out->fronts != nullptr;
+  if (dump && s.FM != 16) return fail(LGAR_E_INVALID, "front dumps need max_fronts = 16");
 #define LGAR_DISPATCH(FM_)                                                         \
-  if (dump) rc = launch_forward<FM_, true, true>(K, st);                           \
-  else if (count) rc = launch_forward<FM_, true, false>(K, st);                    \
+  if (count) rc = launch_forward<FM_, true, false>(K, st);                         \
   else rc = launch_forward<FM_, false, false>(K, st);
-  if (s.FM == 8) { LGAR_DISPATCH(8) }
+  if (dump) rc = launch_forward<16, true, true>(K, st);
+  else if (s.FM == 8) { LGAR_DISPATCH(8) }
   else if (s.FM == 12) { LGAR_DISPATCH(12) }
   else { LGAR_DISPATCH(16) }
 #undef LGAR_DISPATCH
@@ -235,11 +236,10 @@ int lgar_forward_host(const lgar_problem* ph, const lgar_outputs* oh) {
   UP(initial_psi, B) UP(ponded_depth_max, B) UP(forcing, (size_t)ph->num_sites * T * 2) UP(site_index, B)
 #undef UP
 #define AL(field, count) if ((rc = db.alloc(oh->field, (count), &o.field))) return rc;
-  AL(per_step, (size_t)LGAR_NUM_OUTPUTS * T * B) AL(sums, (size_t)LGAR_NUM_OUTPUTS * B) AL(start_volume, B)
+  AL(per_step, (size_t)__builtin_popcount(oh->per_step_mask) * T * B) AL(sums, (size_t)LGAR_NUM_OUTPUTS * B) AL(start_volume, B)
   AL(status, B) AL(crash_step, B) AL(num_fronts, T * B) AL(fronts, T * LGAR_MAX_FRONTS * 5 * B)
   AL(front_layer, T * LGAR_MAX_FRONTS * B) AL(front_to_bottom, T * LGAR_MAX_FRONTS * B) AL(counters, 8)
 #undef AL
-  if (o.per_step) CUDA_TRY(cudaMemset(o.per_step, 0, (size_t)LGAR_NUM_OUTPUTS * T * B * sizeof(double)));
   const size_t wsb = lgar_workspace_bytes(&p, 0);
   void* ws = nullptr;
   CUDA_TRY(cudaMalloc(&ws, wsb));
@@ -249,7 +249,7 @@ int lgar_forward_host(const lgar_problem* ph, const lgar_outputs* oh) {
   CUDA_TRY(cudaDeviceSynchronize());
 #define DOWN(field, count) \
   if (oh->field) CUDA_TRY(cudaMemcpy(oh->field, o.field, (count) * sizeof(*oh->field), cudaMemcpyDeviceToHost));
-  DOWN(per_step, (size_t)LGAR_NUM_OUTPUTS * T * B) DOWN(sums, (size_t)LGAR_NUM_OUTPUTS * B) DOWN(start_volume, B)
+  DOWN(per_step, (size_t)__builtin_popcount(oh->per_step_mask) * T * B) DOWN(sums, (size_t)LGAR_NUM_OUTPUTS * B) DOWN(start_volume, B)
   DOWN(status, B) DOWN(crash_step, B) DOWN(num_fronts, T * B) DOWN(fronts, T * LGAR_MAX_FRONTS * 5 * B)
   DOWN(front_layer, T * LGAR_MAX_FRONTS * B) DOWN(front_to_bottom, T * LGAR_MAX_FRONTS * B) DOWN(counters, 8)
 #undef DOWN

@@ -498,7 +498,8 @@ __global__ void __launch_bounds__(NT) lgar_forward_kernel(const KParams K) {
 #pragma unroll
           for (int k = 0; k < NOUT; k++)
             if (K.o.per_step_mask & (1u << k))
-              K.o.per_step[((size_t)k * Tn + t) * B + b] = ok ? T.acc[k] : qnan;
+              K.o.per_step[((size_t)__popc(K.o.per_step_mask & ((1u << k) - 1u)) * Tn + t) * B + b] =
+                  ok ? T.acc[k] : qnan;
         }
         if (ok) {
 #pragma unroll
