@@ -113,6 +113,45 @@ __device__ __forceinline__ double h_from_se(double se, const Soil& s, Ctx& c) {
   return error_check(r, c);
 }
 
+// ------------------------------------------------------------------------------------
+// Exact result of k successive ROUNDED additions x = fl(x + s) (s may be negative), in
+// O(number of binades crossed) instead of O(k).  Inside one binade every x is a multiple of
+// ulp, so fl(x + s) - x is the same representable increment c for every step unless the
+// discarded part of s is exactly half an ulp (tie -> round-to-even alternates; those steps are
+// taken one by one).  Used by the root finder to jump along a monotone run of psi steps while
+// visiting exactly the psi values the reference's `psi = psi +/- 0.1*factor` loop visits.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ int f64_exponent(double x) { return (__double2hiint(x) >> 20) & 0x7ff; }
+__device__ double advance_rounded(double x, double s, long long k) {
+  while (k > 0) {
+    const double t = x + s;
+    k--;
+    if (k == 0) return t;
+    const int e0 = f64_exponent(x), e1 = f64_exponent(t);
+    const double c = t - x;    // exact (|s| << |x| in every caller)
+    const double err = s - c;  // exact rounding residual of this step
+    if (e0 != e1 || e1 <= 53 || e1 >= 0x7fe || !(t > 0.0)) {
+      x = t;
+      continue;
+    }
+    const double ulp = __hiloint2double((e1 - 52) << 20, 0);
+    if (fabs(err) * 2.0 == ulp || c == 0.0) {
+      if (c == 0.0) return t;  // x + s == x from here on
+      x = t;
+      continue;
+    }
+    // steps that stay strictly inside the binade of t with the constant increment c
+    const double lim = (s > 0.0) ? __hiloint2double((e1 + 1) << 20, 0) : __hiloint2double(e1 << 20, 0);
+    const double room = (s > 0.0) ? (lim - t) : (t - lim);
+    long long n = (long long)floor(room / fabs(c)) - 1;
+    if (n > k) n = k;
+    if (n < 0) n = 0;
+    x = fma((double)n, c, t);  // exact: the result is a multiple of ulp inside the binade
+    k -= n;
+  }
+  return x;
+}
+
 // torch.min / torch.minimum semantics (NaN propagates, unlike fmin)
 __device__ __forceinline__ double tmin(double a, double b) {
   if (isnan(a) || isnan(b)) return a + b;
@@ -317,58 +356,6 @@ struct Column {
     return w;
   }
 
-  // ---- root finder: Layer.theta_mass_balance (Layer.py:242-318) + recalculate_mass (:211-240).
-  //      `lyr` is the layer of the front, `nup` the number of upper layers that take part
-  //      (len(delta_thickness) - 1), dth/dtk the delta_thetas / delta_thickness arrays.
-  __device__ double theta_mass_balance(int lyr, int nup, double psi_cm, double new_mass, double prior_mass,
-                                       const double* dth, const double* dtk, Ctx& c) {
-    const double tol = 1e-12;
-    double delta_mass = fabs(new_mass - prior_mass);
-    bool switched = false;
-    double factor = 1.0;
-    double theta = 0.0;
-    double psi_prev = psi_cm;
-    double delta_mass_prev = delta_mass;
-    int count_no_mass_change = 0;
-    if (delta_mass <= tol) return theta_from_h(psi_cm, soil[lyr], c);
-    long long it = 0;
-    while (delta_mass > tol) {
-      if (++it > c.iter_cap) {
-        raise(c, LGAR_ST_ITER_CAP);
-        break;
-      }
-      c.cnt[C_ROOT]++;
-      if (new_mass > prior_mass) {
-        psi_cm = psi_cm + (0.1 * factor);
-        switched = false;
-      } else {
-        if (!switched) {
-          switched = true;
-          factor = factor * 0.1;
-        }
-        psi_prev = psi_cm;
-        psi_cm = psi_cm - (0.1 * factor);
-        if (psi_cm < 0.0 && psi_prev != 0.0) psi_cm = psi_prev * 0.1;
-      }
-      theta = theta_from_h(psi_cm, soil[lyr], c);
-      double mass_layers = 0.0 + (dtk[lyr] * (theta - dth[lyr]));
-      for (int k = 0; k < nup; k++) {
-        double theta_layer = theta_from_h(psi_cm, soil[k], c);
-        mass_layers = mass_layers + dtk[k] * (theta_layer - dth[k]);
-      }
-      new_mass = mass_layers;
-      delta_mass = fabs(new_mass - prior_mass);
-      if (c.st) break;  // the reference raised inside theta_from_h
-      if (fabs(psi_cm - psi_prev) < 1e-15 && factor < 1e-13) break;
-      if (fabs(delta_mass - delta_mass_prev) < 1e-15) count_no_mass_change++;
-      else count_no_mass_change = 0;
-      if (count_no_mass_change == 5) break;
-      if (psi_cm <= 0.0 && psi_prev < 1e-50) break;
-      delta_mass_prev = delta_mass;
-    }
-    return theta;
-  }
-
   // ---- Layer.check_column_mass (Layer.py:655-701)
   __device__ void check_column_mass(int fd, double old_mass, double percolation, double aet, Ctx& c) {
     const double theta_e_k1 = soil[lay(fd)].the;
@@ -403,57 +390,120 @@ struct Column {
     }
   }
 
-  // ---- Layer.move_wetting_fronts (Layer.py:1254-1307): sweep from the deepest front to the top.
-  //      previous_state[i] of the reference equals the state at entry of this sweep (nothing
-  //      modifies fronts between copy_states() and here), and only the OLD theta/psi of the
-  //      front below (previous_next_front) and the front's own old values are read, so the
-  //      snapshot is carried in two registers instead of a copy of the list.
-  __device__ void move_wetting_fronts(int fd, double infiltration, double aet, double old_mass, double dt, Ctx& c) {
-    const int num_wf = n;
+  // ---- Layer.move_wetting_fronts (Layer.py:1254-1307): sweep from the deepest front to the top,
+  //      WARP-CONVERGENT: every lane of the warp calls it.  Round r handles, in every lane, the r-th
+  //      front counted from the bottom of that lane's column.  All pow-heavy work runs in batched,
+  //      convergent phases:
+  //        P1  upper-layer sums of compute_wetting_front_mass (:561-644) / populate_delta_thickness
+  //            (:177-209)
+  //        P2  Layer.theta_mass_balance (:242-318) + recalculate_mass (:211-240): one root-finder
+  //            iteration per warp pass for every lane that has a request; the sequence of psi values
+  //            a lane visits is exactly the reference's
+  //        P3  psi = h(Se(theta)) tail
+  //      previous_state[i] of the reference equals the state at entry of this sweep (nothing modifies
+  //      fronts between copy_states() and here), and only the OLD theta/psi of the front below
+  //      (previous_next_front) and the front's own old values are read, so the snapshot is carried in
+  //      registers instead of a copy of the list.
+  enum Kind { K_NONE = 0, K_DEEPEST = 1, K_INLAYER0 = 2, K_INLAYER_DEEP = 3, K_BASE = 4 };
+
+  __device__ void move_wetting_fronts_warp(bool go, int fd, double infiltration, double aet, double old_mass,
+                                           double dt, Ctx& c) {
+    const unsigned FULL = 0xffffffffu;
+    go = go && (c.st == 0);
+    const int num_wf = go ? n : 0;
+    int rmax = num_wf;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) rmax = max(rmax, __shfl_xor_sync(FULL, rmax, d));
     double old_theta_below = 0.0, old_psi_below = 0.0;  // previous_state of front i+1
     int l = L - 1;
-    int o = n - cnt(L - 1);  // flat offset of list l
-    for (int i = n - 1; i >= 0; i--) {
-      while (i < o) {  // step to the list above
-        l--;
-        o -= cnt(l);
-      }
-      const int last = o + cnt(l) - 1;  // wetting_fronts[-1] of this list
-      const double old_depth = f(F_DEPTH, i), old_theta = f(F_THETA, i), old_psi = f(F_PSI, i);
-      const Soil& s = soil[l];
-      if (i < num_wf - 1) {
-        if (is_equal(i, last)) {
-          // deepest_layer_front (Layer.py:389-418): next_front = first front of the layer below
-          // (i == last), or wetting_fronts[i+1] when a non-last front is value-equal to the last
-          if (!(i < last || l < L - 1)) raise(c, LGAR_ST_NULL_NEIGHBOUR);
-          const double psi_next = f(F_PSI, i + 1);
-          f(F_THETA, i) = theta_from_h(psi_next, s, c);
-          f(F_PSI, i) = psi_next;
-        } else {
-          // wetting_front_in_layer (Layer.py:420-547); here i < last so next is in the same list
-          const double dzdt = f(F_DZDT, i);
-          if (l == 0) {
-            double prior_mass = old_depth * (old_theta - old_theta_below);
-            if (is_equal(fd, i)) prior_mass = prior_mass + (infiltration - (0.0 + aet));
-            double depth = old_depth + (dzdt * dt);
-            depth = tmin(depth, cum[L - 1]);
-            f(F_DEPTH, i) = depth;
-            const bool zero_dzdt = fabs(dzdt) <= 1e-8;  // isclose(dzdt, 0, rtol=1e-8) (Q2)
-            if (!(zero_dzdt && !tb(i))) {
-              double potential_theta = (prior_mass / depth) + f(F_THETA, i + 1);
-              f(F_THETA, i) = tmin(s.the, potential_theta);
-            }
+    int o = go ? n - cnt(L - 1) : 0;  // flat offset of list l
+    for (int r = 0; r < rmax; r++) {
+      const int i = num_wf - 1 - r;
+      const bool mine = go && (i >= 0) && (c.st == 0);
+      int kind = K_NONE, lyr = 0, nup = 0;
+      bool add_flux = false;
+      double psi_cm = 0.0, psi_old = 0.0, psi_below = 0.0, psi_below_old = 0.0;
+      double prior_mass = 0.0, new_mass = 0.0, own_dth = 0.0, own_dtk = 0.0;
+      double old_depth = 0.0, old_theta = 0.0, old_psi = 0.0;
+      if (mine) {
+        while (i < o) {  // step to the list above
+          l--;
+          o -= cnt(l);
+        }
+        lyr = l;
+        const int last = o + cnt(l) - 1;  // wetting_fronts[-1] of this list
+        old_depth = f(F_DEPTH, i);
+        old_theta = f(F_THETA, i);
+        old_psi = f(F_PSI, i);
+        if (i < num_wf - 1) {
+          if (is_equal(i, last)) {
+            // deepest_layer_front (Layer.py:389-418): theta = theta_l(psi of the front below)
+            if (!(i < last || l < L - 1)) raise(c, LGAR_ST_NULL_NEIGHBOUR);
+            kind = K_DEEPEST;
+            psi_cm = f(F_PSI, i + 1);
           } else {
-            const double plt = cum[l - 1];
-            const double depth = old_depth + (dzdt * dt);
-            f(F_DEPTH, i) = depth;
-            const double psi_old = old_psi, psi_below_old = old_psi_below;
-            const double psi_cm = old_psi, psi_below = f(F_PSI, i + 1);
-            double prior_mass = (old_depth - plt) * (old_theta - old_theta_below);
-            double new_mass = (depth - plt) * (old_theta - f(F_THETA, i + 1));
-            double dth[MAXL], dtk[MAXL];
-            for (int k = 0; k < l; k++) {  // compute_wetting_front_mass (Layer.py:561-644)
-              const Soil& sk = soil[k];
+            // wetting_front_in_layer (Layer.py:420-547); i < last, so next is in the same list
+            const double dzdt = f(F_DZDT, i);
+            if (l == 0) {
+              kind = K_INLAYER0;
+              double pm = old_depth * (old_theta - old_theta_below);
+              if (is_equal(fd, i)) pm = pm + (infiltration - (0.0 + aet));
+              double depth = old_depth + (dzdt * dt);
+              depth = tmin(depth, cum[L - 1]);
+              f(F_DEPTH, i) = depth;
+              const bool zero_dzdt = fabs(dzdt) <= 1e-8;  // isclose(dzdt, 0, rtol=1e-8) (Q2)
+              if (!(zero_dzdt && !tb(i))) {
+                double potential_theta = (pm / depth) + f(F_THETA, i + 1);
+                f(F_THETA, i) = tmin(soil[0].the, potential_theta);
+              }
+            } else {
+              kind = K_INLAYER_DEEP;
+              const double plt = cum[l - 1];
+              const double depth = old_depth + (dzdt * dt);
+              f(F_DEPTH, i) = depth;
+              psi_old = old_psi;
+              psi_below_old = old_psi_below;
+              psi_cm = old_psi;
+              psi_below = f(F_PSI, i + 1);
+              prior_mass = (old_depth - plt) * (old_theta - old_theta_below);
+              new_mass = (depth - plt) * (old_theta - f(F_THETA, i + 1));
+              nup = l;
+              own_dth = f(F_THETA, i + 1);
+              own_dtk = depth - plt;
+              add_flux = is_equal(fd, i);
+            }
+          }
+        }
+        if (num_wf == L && l == L - 1) {
+          // base_case (Layer.py:320-387): one front per layer, this is the bottom one
+          kind = K_BASE;
+          const double depth = f(F_DEPTH, i) + f(F_DZDT, i) * dt;
+          f(F_DEPTH, i) = depth;
+          psi_old = old_psi;
+          psi_cm = f(F_PSI, i);
+          const double base = (l > 0) ? cum[l - 1] : 0.0;
+          prior_mass = (old_depth - base) * (old_theta - 0.0);
+          new_mass = (depth - base) * (f(F_THETA, i) - 0.0);
+          if (L < 2) raise(c, LGAR_ST_NULL_NEIGHBOUR);
+          nup = L - 1;
+          own_dth = 0.0;
+          own_dtk = depth - base;
+          add_flux = (lay(fd) == l);
+        }
+      }
+      // ---- P1: sums over the layers above (convergent)
+      double dth[MAXL - 1], dtk[MAXL - 1];
+      int nupmax = nup;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) nupmax = max(nupmax, __shfl_xor_sync(FULL, nupmax, d));
+#pragma unroll
+      for (int k = 0; k < MAXL - 1; k++) {
+        dth[k] = 0.0;
+        dtk[k] = 0.0;
+        if (k < nupmax) {
+          if (k < nup) {
+            const Soil& sk = soil[k];
+            if (kind == K_INLAYER_DEEP) {
               double theta_old = theta_from_h(psi_old, sk, c);
               double theta_below_old = theta_from_h(psi_below_old, sk, c);
               double local_delta_old = theta_old - theta_below_old;
@@ -464,47 +514,166 @@ struct Column {
               new_mass = new_mass + (layer_thickness * (theta - theta_below));
               dth[k] = theta_below;
               dtk[k] = layer_thickness;
+            } else {  // K_BASE
+              double theta_old = theta_from_h(psi_old, sk, c);
+              prior_mass = prior_mass + thick[k] * (theta_old - 0.0);
+              double theta = theta_from_h(psi_cm, sk, c);
+              new_mass = new_mass + thick[k] * (theta - 0.0);
+              dth[k] = 0.0;
+              dtk[k] = thick[k];
             }
-            dth[l] = f(F_THETA, i + 1);
-            dtk[l] = depth - plt;
-            if (is_equal(fd, i)) prior_mass = prior_mass + infiltration - (0.0 + aet);
-            double theta_new = theta_mass_balance(l, l, psi_cm, new_mass, prior_mass, dth, dtk, c);
-            f(F_THETA, i) = tmin(theta_new, s.the);
           }
-          double se = se_from_theta(f(F_THETA, i), s, c);
-          f(F_PSI, i) = h_from_se(se, s, c);
         }
       }
-      if (num_wf == L && l == L - 1) {
-        // base_case (Layer.py:320-387) + populate_delta_thickness (:177-209)
-        const double depth = f(F_DEPTH, i) + f(F_DZDT, i) * dt;
-        f(F_DEPTH, i) = depth;
-        const double psi_old = old_psi, psi_cm = f(F_PSI, i);
-        const double base = (l > 0) ? cum[l - 1] : 0.0;
-        double prior_mass = (old_depth - base) * (old_theta - 0.0);
-        double new_mass = (depth - base) * (f(F_THETA, i) - 0.0);
-        double dth[MAXL], dtk[MAXL];
-        if (L < 2) raise(c, LGAR_ST_NULL_NEIGHBOUR);
-        for (int k = 0; k < L - 1; k++) {
-          const Soil& sk = soil[k];
-          double theta_old = theta_from_h(psi_old, sk, c);
-          prior_mass = prior_mass + thick[k] * (theta_old - 0.0);
-          double theta = theta_from_h(psi_cm, sk, c);
-          new_mass = new_mass + thick[k] * (theta - 0.0);
-          dth[k] = 0.0;
-          dtk[k] = thick[k];
+      if (add_flux) prior_mass = prior_mass + infiltration - (0.0 + aet);
+
+      // ---- P2: batched theta_mass_balance
+      const double tol = 1e-12;
+      const Soil own = soil[lyr];
+      double delta_mass = fabs(new_mass - prior_mass);
+      double theta = 0.0;
+      const bool wants = mine && (kind == K_DEEPEST || kind >= K_INLAYER_DEEP) && (c.st == 0);
+      // early return `delta_mass <= tolerance` (and the deepest-front case): one evaluation
+      if (wants && (kind == K_DEEPEST || delta_mass <= tol)) theta = theta_from_h(psi_cm, own, c);
+      bool active = wants && kind >= K_INLAYER_DEEP && (delta_mass > tol);
+      {
+        bool switched = false;
+        double factor = 1.0;
+        double psi_prev = psi_cm;
+        double delta_mass_prev = delta_mass;
+        int count_no_mass_change = 0;
+        long long it = 0;
+        // run tracking for the exact jump: a "run" is a maximal sequence of iterations that step psi
+        // in the same direction with the same step.  Only the coarse runs (step 0.1 or 0.01) can be
+        // long (psi travelling hundreds of cm after a wetting/drying event); they are crossed by
+        // doubling/halving probes on psi values computed with advance_rounded(), so the lane lands on
+        // exactly the psi the reference's one-step-at-a-time loop reaches before the run ends.
+        int run_len = 0;        // regular iterations taken so far in the current run
+        bool run_up = false;
+        long long stride = 0;   // > 0: next pass is a probe `stride` steps ahead
+        bool shrinking = false, run_jumped = false;
+        while (__any_sync(FULL, active)) {
+          if (active) {
+            if (it > c.iter_cap) {
+              raise(c, LGAR_ST_ITER_CAP);
+              active = false;
+            }
+          }
+          if (active) {
+            c.cnt[C_ROOT]++;
+            const bool probe = stride >= 2;
+            const bool up = probe ? run_up : (new_mass > prior_mass);
+            double step;
+            double psi_try, psi_prev_try = psi_prev;
+            bool sw = switched;
+            double fac = factor;
+            if (probe) {
+              step = 0.1 * factor;
+              psi_try = advance_rounded(psi_cm, up ? step : -step, stride);
+              if (!up) psi_prev_try = advance_rounded(psi_cm, -step, stride - 1);
+            } else if (up) {
+              step = 0.1 * factor;
+              psi_try = psi_cm + step;
+              sw = false;
+            } else {
+              if (!sw) {
+                sw = true;
+                fac = fac * 0.1;
+              }
+              step = 0.1 * fac;
+              psi_prev_try = psi_cm;
+              psi_try = psi_cm - step;
+              if (psi_try < 0.0 && psi_prev_try != 0.0) psi_try = psi_prev_try * 0.1;
+            }
+            Ctx cc;  // guards raised by a rejected probe must not kill the column
+            cc.st = 0;
+            cc.cnt[C_THETA_H] = 0;
+            const double th = theta_from_h(psi_try, own, cc);
+            double mass_layers = 0.0 + (own_dtk * (th - own_dth));
+#pragma unroll
+            for (int k = 0; k < MAXL - 1; k++) {
+              if (k < nup) {
+                double theta_layer = theta_from_h(psi_try, soil[k], cc);
+                mass_layers = mass_layers + dtk[k] * (theta_layer - dth[k]);
+              }
+            }
+            c.cnt[C_THETA_H] += cc.cnt[C_THETA_H];
+            const double dm = fabs(mass_layers - prior_mass);
+            if (probe) {
+              const bool cont = up ? (mass_layers > prior_mass) : (mass_layers <= prior_mass);
+              const bool ok = cont && cc.st == 0 && dm > tol && (psi_try > 64.0 * step) &&
+                              fabs(mass_layers - new_mass) >= 1e-12 * (double)stride;
+              if (ok) {  // identical to `stride` regular iterations of this run
+                psi_cm = psi_try;
+                psi_prev = psi_prev_try;
+                theta = th;
+                new_mass = mass_layers;
+                delta_mass = dm;
+                delta_mass_prev = dm;
+                count_no_mass_change = 0;
+                it += stride;
+                stride = shrinking ? (stride >> 1) : (stride << 1);
+                if (stride > (1LL << 40)) stride = 1LL << 40;
+              } else {
+                shrinking = true;
+                stride >>= 1;
+              }
+              if (stride < 2) stride = 0;
+            } else {
+              it++;
+              if (cc.st) raise(c, cc.st);  // the reference raised inside theta_from_h
+              if (run_len > 0 && up == run_up && fac == factor) run_len++;
+              else {
+                run_len = 1;
+                run_up = up;
+                run_jumped = false;
+                shrinking = false;
+              }
+              psi_cm = psi_try;
+              psi_prev = psi_prev_try;
+              switched = sw;
+              factor = fac;
+              theta = th;
+              new_mass = mass_layers;
+              delta_mass = dm;
+              bool stop = !(delta_mass > tol);
+              if (c.st) stop = true;
+              if (fabs(psi_cm - psi_prev) < 1e-15 && factor < 1e-13) stop = true;
+              if (fabs(delta_mass - delta_mass_prev) < 1e-15) count_no_mass_change++;
+              else count_no_mass_change = 0;
+              if (count_no_mass_change == 5) stop = true;
+              if (psi_cm <= 0.0 && psi_prev < 1e-50) stop = true;
+              delta_mass_prev = delta_mass;
+              if (stop) active = false;
+              // start probing if the run goes on: same direction next, coarse step, far from psi = 0
+              else if (run_len >= 3 && !run_jumped && factor >= 0.05 && (new_mass > prior_mass) == run_up &&
+                       count_no_mass_change == 0 && psi_cm > 64.0 * (0.1 * factor)) {
+                stride = 4;
+                shrinking = false;
+                run_jumped = true;
+              }
+            }
+          }
         }
-        dth[l] = 0.0;
-        dtk[l] = depth - base;
-        if (lay(fd) == l) prior_mass = prior_mass + infiltration - (0.0 + aet);
-        double theta_new = theta_mass_balance(l, L - 1, psi_cm, new_mass, prior_mass, dth, dtk, c);
-        f(F_THETA, i) = tmin(theta_new, s.the);
-        double se = se_from_theta(f(F_THETA, i), s, c);
-        f(F_PSI, i) = h_from_se(se, s, c);
       }
-      if (i == 0) check_column_mass(fd, old_mass, infiltration, aet, c);
-      old_theta_below = old_theta;
-      old_psi_below = old_psi;
+      // ---- P3: store theta, psi = h(Se(theta)) tail
+      if (mine && c.st == 0) {
+        if (kind == K_DEEPEST) {
+          f(F_THETA, i) = theta;
+          f(F_PSI, i) = psi_cm;
+        } else if (kind >= K_INLAYER_DEEP) {
+          f(F_THETA, i) = tmin(theta, own.the);
+        }
+      }
+      if (mine && kind >= K_INLAYER0 && c.st == 0) {
+        double se = se_from_theta(f(F_THETA, i), own, c);
+        f(F_PSI, i) = h_from_se(se, own, c);
+      }
+      if (mine) {
+        if (i == 0 && c.st == 0) check_column_mass(fd, old_mass, infiltration, aet, c);
+        old_theta_below = old_theta;
+        old_psi_below = old_psi;
+      }
     }
   }
 
@@ -725,18 +894,26 @@ struct Column {
     raise(c, LGAR_ST_INDEX_ERROR);
   }
 
-  // ---- Layer.update_psi (Layer.py:1157-1174)
-  __device__ void update_psi(Ctx& c) {
-    int o = 0;
-    for (int l = 0; l < L; l++) {
-      const int lf = len_layers(l);
-      const Soil& s = soil[l];
-      for (int j = 0; j < lf; j++) {
-        double se = se_from_theta(f(F_THETA, o + j), s, c);
-        f(F_PSI, o + j) = h_from_se(se, s, c);
-        f(F_K, o + j) = k_from_se(se, s.ksat, s.m, s.inv_m, c);
+  // ---- Layer.update_psi (Layer.py:1157-1174): psi, K from theta for every front except the deepest
+  //      of the domain.  Warp-convergent flat loop over the front index.
+  __device__ void update_psi_warp(bool go, Ctx& c) {
+    go = go && (c.st == 0);
+    const int my_n = go ? n - 1 : 0;
+    int nmax = my_n;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, d));
+    int l = 0, o_next = go ? cnt(0) : 0;
+    for (int i = 0; i < nmax; i++) {
+      if (i < my_n) {
+        while (i >= o_next) {
+          l++;
+          o_next += cnt(l);
+        }
+        const Soil& s = soil[l];
+        double se = se_from_theta(f(F_THETA, i), s, c);
+        f(F_PSI, i) = h_from_se(se, s, c);
+        f(F_K, i) = k_from_se(se, s.ksat, s.m, s.inv_m, c);
       }
-      o += cnt(l);
     }
   }
 
@@ -757,17 +934,21 @@ struct Column {
     }
   }
 
-  // ---- dpLGAR.move_wetting_front (models/dpLGAR.py:340-367); returns the bottom flux
-  __device__ double move_wetting_front(int fd, double infiltration, double& AET_sub, double old_mass, double dt,
-                                       Ctx& c) {
-    move_wetting_fronts(fd, infiltration, AET_sub, old_mass, dt, c);
-    merge_wetting_fronts(c);
-    cross_layer_boundary(c);
-    merge_wetting_fronts(c);
-    double bottom_flux = 0.0 + cross_domain_boundary(c);
-    double mass_change = fix_dry_over_wet(c);
-    if (fabs(mass_change) > 1e-7) AET_sub = AET_sub - mass_change;
-    update_psi(c);
+  // ---- dpLGAR.move_wetting_front (models/dpLGAR.py:340-367); returns the bottom flux.
+  //      Warp-convergent (every lane calls; `go` selects the lanes that actually move fronts).
+  __device__ double move_wetting_front_warp(bool go, int fd, double infiltration, double& AET_sub, double old_mass,
+                                            double dt, Ctx& c) {
+    move_wetting_fronts_warp(go, fd, infiltration, AET_sub, old_mass, dt, c);
+    double bottom_flux = 0.0;
+    if (go && c.st == 0) {
+      merge_wetting_fronts(c);
+      cross_layer_boundary(c);
+      merge_wetting_fronts(c);
+      bottom_flux = 0.0 + cross_domain_boundary(c);
+      double mass_change = fix_dry_over_wet(c);
+      if (fabs(mass_change) > 1e-7) AET_sub = AET_sub - mass_change;
+    }
+    update_psi_warp(go, c);
     return bottom_flux;
   }
 };

@@ -205,10 +205,11 @@ __device__ void substep(Tile<FM>& T, bool act, double precip_rate, double pet_ra
 
   // ---- phase 2: move the fronts (branch A moves without adding water; every non-create lane moves
   //      with its infiltration).  models/dpLGAR.py:206-212 and :249-266
-  if (act && c.st == 0 && (brA || !create)) {
+  {
+    const bool go = act && c.st == 0 && (brA || !create);
     const double infil_arg = create ? 0.0 : infiltration_sub;
-    const double bottom = C.move_wetting_front(fd, infil_arg, AET_sub, ending_volume_sub, dt, c);
-    if (!create) {
+    const double bottom = C.move_wetting_front_warp(go, fd, infil_arg, AET_sub, ending_volume_sub, dt, c);
+    if (go && !create) {
       percolation_sub = bottom;
       T.acc[LGAR_OUT_PERCOLATION] = T.acc[LGAR_OUT_PERCOLATION] + percolation_sub;
     }  // branch A drops the bottom flux (Q7)
