@@ -135,6 +135,8 @@ typedef struct lgar_outputs {
    * 3 k_from_se, 4 se_from_h, 5 theta root-finder iterations, 6 column-mass iterations,
    * 7 sub-steps.  Used for the algorithmic FLOP count of the roofline.            */
   unsigned long long* counters; /* [8]                                                          */
+  /* diagnostics: SM cycles spent on each tile of 32 consecutive columns, summed over chunks     */
+  unsigned long long* tile_cycles; /* [ceil(B/32)]                                              */
 } lgar_outputs;
 
 /* Library / device probe.  Returns 0 if an sm_100 device is current and usable.               */

@@ -125,6 +125,7 @@ class ForwardResult:
     front_layer: Optional[torch.Tensor] = None     # [T,16,B]
     front_to_bottom: Optional[torch.Tensor] = None # [T,16,B]
     counters: Optional[torch.Tensor] = None        # [8] int64
+    tile_cycles: Optional[torch.Tensor] = None     # [ceil(B/32)] int64 (diagnostics)
 
     def __getitem__(self, name) -> torch.Tensor:
         k = OUT_NAMES.index(name)
@@ -140,7 +141,7 @@ def _param(x, ens: ColumnEnsemble):
 
 
 def forward_raw(ens: ColumnEnsemble, alpha, n, ksat, outputs=("runoff", "percolation"), per_step=True,
-                num_fronts=False, dump_fronts=False, counters=False, keep_checkpoints=False,
+                num_fronts=False, dump_fronts=False, counters=False, tile_cycles=False, keep_checkpoints=False,
                 workspace: Optional[torch.Tensor] = None) -> tuple[ForwardResult, torch.Tensor]:
     """One persistent launch over all columns and all forcing steps (no autograd)."""
     L_ = _capi.lib()
@@ -177,6 +178,9 @@ def forward_raw(ens: ColumnEnsemble, alpha, n, ksat, outputs=("runoff", "percola
     if counters or dump_fronts:
         res.counters = torch.zeros(8, dtype=torch.int64, device=dev)
         o.counters = res.counters.data_ptr()
+    if tile_cycles:
+        res.tile_cycles = torch.zeros((B + 31) // 32, dtype=torch.int64, device=dev)
+        o.tile_cycles = res.tile_cycles.data_ptr()
     stream = torch.cuda.current_stream(dev).cuda_stream
     with torch.cuda.device(dev):
         rc = L_.lgar_forward(C.byref(p), C.byref(o), workspace.data_ptr(), workspace.numel(),

@@ -122,11 +122,11 @@ __device__ __forceinline__ double h_from_se(double se, const Soil& s, Ctx& c) {
 // visiting exactly the psi values the reference's `psi = psi +/- 0.1*factor` loop visits.
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ int f64_exponent(double x) { return (__double2hiint(x) >> 20) & 0x7ff; }
-__device__ double advance_rounded(double x, double s, long long k) {
+__device__ double advance_rounded_pos(double x, double s, long long k) {
   while (k > 0) {
     const double t = x + s;
     k--;
-    if (k == 0) return t;
+    if (k == 0 || !(t > 0.0)) return t;  // callers reject non-positive results
     const int e0 = f64_exponent(x), e1 = f64_exponent(t);
     const double c = t - x;    // exact (|s| << |x| in every caller)
     const double err = s - c;  // exact rounding residual of this step
@@ -150,6 +150,11 @@ __device__ double advance_rounded(double x, double s, long long k) {
     k -= n;
   }
   return x;
+}
+
+// round-to-nearest-even is symmetric under negation, so negative x mirror the positive case
+__device__ __forceinline__ double advance_rounded(double x, double s, long long k) {
+  return (x < 0.0) ? -advance_rounded_pos(-x, -s, k) : advance_rounded_pos(x, s, k);
 }
 
 // torch.min / torch.minimum semantics (NaN propagates, unlike fmin)
@@ -263,6 +268,7 @@ struct Column {
   double psi_wp;     // AET: capillary head at which AET = 0.5 PET (aet.py:37-43); column constant
   double ponded_water, previous_precip, ending_volume;
   double giuh[NGIUH];
+  bool empty_list;   // set by mass_balance() when a layer list is empty (IndexError in the reference)
 
   __device__ __forceinline__ double& f(int fld, int i) { return fb[(fld * FM + i) * NT]; }
   __device__ __forceinline__ int lay(int i) const { return gb[i * NT] & 7; }
@@ -317,6 +323,7 @@ struct Column {
   // ---- Layer.mass_balance (Layer.py:795-824); association S0 + (S1 + (S2 ...))
   __device__ double mass_balance() {
     double s_l[MAXL];
+    empty_list = false;
     int o = 0;
     for (int l = 0; l < L; l++) {
       const double base = (l == 0) ? 0.0 : (cum[l] - thick[l]);
@@ -324,7 +331,8 @@ struct Column {
       double sum = 0.0;
       for (int i = 0; i < nf - 1; i++)
         sum = sum + (f(F_DEPTH, o + i) - base) * (f(F_THETA, o + i) - f(F_THETA, o + i + 1));
-      sum = sum + (f(F_DEPTH, o + nf - 1) - base) * f(F_THETA, o + nf - 1);
+      if (nf > 0) sum = sum + (f(F_DEPTH, o + nf - 1) - base) * f(F_THETA, o + nf - 1);
+      else empty_list = true;  // wetting_fronts[0] of an empty list: IndexError in the reference
       s_l[l] = sum;
       o += nf;
     }
@@ -356,7 +364,11 @@ struct Column {
     return w;
   }
 
-  // ---- Layer.check_column_mass (Layer.py:655-701)
+  // ---- Layer.check_column_mass (Layer.py:655-701): if the free-drainage front is saturated, its
+  //      depth is stepped by +/-0.01*factor (factor *= 0.001 at every down-switch) until the column
+  //      mass error lies in [0, 2e-12].  The column mass is monotone in that depth, so long runs of
+  //      equal steps are crossed with doubling/halving probes on depths computed by
+  //      advance_rounded(): the visited depths are exactly the reference's.
   __device__ void check_column_mass(int fd, double old_mass, double percolation, double aet, Ctx& c) {
     const double theta_e_k1 = soil[lay(fd)].the;
     const double mass_timestep = (old_mass + percolation) - (aet + 0.0);
@@ -367,13 +379,17 @@ struct Column {
       double factor = 1.0;
       double depth_new = f(F_DEPTH, fd);
       long long it = 0;
+      int run_len = 0;
+      bool run_up = false;
       while (fabs(err - 1e-12) > 1e-12) {
         if (++it > c.iter_cap) {
           raise(c, LGAR_ST_ITER_CAP);
           break;
         }
         c.cnt[C_COLMASS]++;
-        if (current_mass < mass_timestep) {
+        const bool up = current_mass < mass_timestep;
+        const double fac_before = factor;
+        if (up) {
           depth_new = depth_new + 0.01 * factor;
           switched = false;
         } else {
@@ -386,6 +402,40 @@ struct Column {
         f(F_DEPTH, fd) = depth_new;
         current_mass = mass_balance();
         err = fabs(current_mass - mass_timestep);
+        if (up == run_up && factor == fac_before) run_len++;
+        else {
+          run_len = 1;
+          run_up = up;
+        }
+        if (run_len >= 3 && fabs(err - 1e-12) > 1e-12 && (current_mass < mass_timestep) == run_up &&
+            fabs(depth_new) >= 64.0 * (0.01 * factor)) {
+          run_len = 0;  // re-armed after three more regular steps of the same run
+          const double step = 0.01 * factor;
+          long long stride = 4;
+          bool shrinking = false;
+          while (stride >= 2) {
+            c.cnt[C_COLMASS]++;
+            const double cand = advance_rounded(depth_new, up ? step : -step, stride);
+            f(F_DEPTH, fd) = cand;
+            const double m = mass_balance();
+            const double e = fabs(m - mass_timestep);
+            const bool cont = (up ? (m < mass_timestep) : !(m < mass_timestep)) && (fabs(e - 1e-12) > 1e-12) &&
+                              (fabs(cand) >= 64.0 * step) && ((cand < 0.0) == (depth_new < 0.0)) &&
+                              fabs(m - current_mass) >= 1e-13 * (double)stride;
+            if (cont) {  // identical to `stride` regular iterations of this run
+              depth_new = cand;
+              current_mass = m;
+              err = e;
+              it += stride;
+              stride = shrinking ? (stride >> 1) : (stride << 1);
+              if (stride > (1LL << 40)) stride = 1LL << 40;
+            } else {
+              shrinking = true;
+              stride >>= 1;
+            }
+          }
+          f(F_DEPTH, fd) = depth_new;
+        }
       }
     }
   }
@@ -551,7 +601,7 @@ struct Column {
         int run_len = 0;        // regular iterations taken so far in the current run
         bool run_up = false;
         long long stride = 0;   // > 0: next pass is a probe `stride` steps ahead
-        bool shrinking = false, run_jumped = false;
+        bool shrinking = false;
         while (__any_sync(FULL, active)) {
           if (active) {
             if (it > c.iter_cap) {
@@ -622,12 +672,10 @@ struct Column {
             } else {
               it++;
               if (cc.st) raise(c, cc.st);  // the reference raised inside theta_from_h
-              if (run_len > 0 && up == run_up && fac == factor) run_len++;
+              if (up == run_up && fac == factor) run_len++;
               else {
                 run_len = 1;
                 run_up = up;
-                run_jumped = false;
-                shrinking = false;
               }
               psi_cm = psi_try;
               psi_prev = psi_prev_try;
@@ -646,11 +694,11 @@ struct Column {
               delta_mass_prev = delta_mass;
               if (stop) active = false;
               // start probing if the run goes on: same direction next, coarse step, far from psi = 0
-              else if (run_len >= 3 && !run_jumped && factor >= 0.05 && (new_mass > prior_mass) == run_up &&
+              else if (run_len >= 3 && factor >= 0.05 && (new_mass > prior_mass) == run_up &&
                        count_no_mass_change == 0 && psi_cm > 64.0 * (0.1 * factor)) {
                 stride = 4;
                 shrinking = false;
-                run_jumped = true;
+                run_len = 0;  // re-armed after three more regular steps of the same run
               }
             }
           }
@@ -811,26 +859,52 @@ struct Column {
     }
   }
 
-  // ---- Layer.wetting_front_cross_domain_boundary (Layer.py:1010-1053).  Unreachable in any
-  //      reference run that completes (Q9); if its condition ever holds the column is flagged.
+  // ---- Layer.wetting_front_cross_domain_boundary (Layer.py:1010-1053): a front without a
+  //      next_to_next neighbour that lies below its layer leaves the domain: its water becomes the
+  //      bottom flux, the front below inherits its theta (psi, K recomputed with THIS layer's
+  //      parameters, sic) and it is popped.  Reachable for the last front of layer L-2 when the
+  //      last layer holds a single front.  The loop bound is evaluated before the pops, like
+  //      Python's range(): an index past the shortened list raises IndexError.
   __device__ double cross_domain_boundary(Ctx& c) {
+    double fl[MAXL];
     int o = 0;
     for (int l = 0; l < L; l++) {
+      fl[l] = 0.0;
       const int lf = len_layers(l);
+      const Soil& s = soil[l];
       for (int j = 0; j < lf; j++) {
+        if (j >= cnt(l)) {
+          raise(c, LGAR_ST_INDEX_ERROR);
+          return 0.0;
+        }
         const int n2 = next_to_next(l, o, j);
         if (n2 == -2) {
           raise(c, LGAR_ST_NULL_NEIGHBOUR);
           return 0.0;
         }
-        if (n2 == -1 && f(F_DEPTH, o + j) > cum[l]) {
-          raise(c, LGAR_ST_BOTTOM_REACHED);
-          return 0.0;
+        double tmp = 0.0;
+        const int i = o + j;
+        if (n2 == -1 && f(F_DEPTH, i) > cum[l]) {
+          const bool has_next = (j < cnt(l) - 1) || (l < L - 1);
+          if (!has_next) {
+            raise(c, LGAR_ST_NULL_NEIGHBOUR);
+            return 0.0;
+          }
+          const int nx = i + 1;
+          tmp = (f(F_THETA, i) - f(F_THETA, nx)) * (f(F_DEPTH, i) - f(F_DEPTH, nx));
+          f(F_THETA, nx) = f(F_THETA, i);
+          double se_k = se_from_theta(f(F_THETA, i), s, c);
+          f(F_PSI, nx) = h_from_se(se_k, s, c);
+          f(F_K, nx) = k_from_se(se_k, s.ksat, s.m, s.inv_m, c);
+          erase_at(i, l);
         }
+        fl[l] = fl[l] + tmp;
       }
       o += cnt(l);
     }
-    return 0.0;
+    double tot = fl[L - 1];
+    for (int l = L - 2; l >= 0; l--) tot = fl[l] + tot;
+    return tot;
   }
 
   // ---- Layer.fix_dry_over_wet_fronts (Layer.py:1055-1143): one fix per layer list per call
@@ -945,7 +1019,12 @@ struct Column {
       cross_layer_boundary(c);
       merge_wetting_fronts(c);
       bottom_flux = 0.0 + cross_domain_boundary(c);
-      double mass_change = fix_dry_over_wet(c);
+      // a layer list emptied by the pop above: the very next neighbour lookup of the reference
+      // (fix_dry_over_wet_fronts -> get_neighboring_fronts / mass_balance) raises IndexError
+      for (int l = 0; l < L; l++)
+        if (cnt(l) == 0) raise(c, LGAR_ST_INDEX_ERROR);
+      double mass_change = 0.0;
+      if (c.st == 0) mass_change = fix_dry_over_wet(c);
       if (fabs(mass_change) > 1e-7) AET_sub = AET_sub - mass_change;
     }
     update_psi_warp(go, c);

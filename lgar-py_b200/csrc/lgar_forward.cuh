@@ -465,6 +465,7 @@ __global__ void __launch_bounds__(NT) lgar_forward_kernel(const KParams K) {
     }
 #pragma unroll
     for (int k = 0; k < 8; k++) T.ctx.cnt[k] = 0;
+    const long long clk0 = clock64();
     load_params(K, bb, T);
     const int slot_in = K.keep_ckpt ? chunk : 0;
     if (chunk == 0) {
@@ -539,7 +540,10 @@ __global__ void __launch_bounds__(NT) lgar_forward_kernel(const KParams K) {
     }
     __threadfence();
     __syncwarp();
-    if (lane == 0) atomicExch(K.done + tile, chunk + 1);
+    if (lane == 0) {
+      if (K.o.tile_cycles) atomicAdd(K.o.tile_cycles + tile, (unsigned long long)(clock64() - clk0));
+      atomicExch(K.done + tile, chunk + 1);
+    }
   }
 }
 

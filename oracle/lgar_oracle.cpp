@@ -385,6 +385,10 @@ struct Column {
       for (auto* f : ly.wf) ly.prev.push_back(*f);
     }
   }
+  Front<T>* first_front(int l) {  // layers[l].wetting_fronts[0]; IndexError on an empty list
+    if (layers[l].wf.empty()) throw RefError{ST_INDEX_ERROR};
+    return layers[l].wf[0];
+  }
   int num_fronts() const {  // Layer.calc_num_wetting_fronts (Layer.py:171-175)
     int n = 0;
     for (auto& ly : layers) n += (int)ly.wf.size();
@@ -415,7 +419,7 @@ struct Column {
 
   // ---- free-drainage front: models/dpLGAR.py:328-338 + Layer.py:134-162
   Front<T>* calc_wetting_front_free_drainage() {
-    Front<T>* w = layers[0].wf[0];
+    Front<T>* w = first_front(0);
     T psi = w->psi;
     for (auto& ly : layers) {
       for (auto* cf : ly.wf) {
@@ -450,7 +454,7 @@ struct Column {
       nb.pnext = &ly.prev[i + 1];
     }
     if (ly.l < L - 1 && i == nf - 1) {
-      nb.next = layers[ly.l + 1].wf[0];
+      nb.next = first_front(ly.l + 1);
       nb.pnext = &ly.prev[0];  // sic (Q4): previous_state[0] of the SAME layer
     }
     return nb;
@@ -465,9 +469,9 @@ struct Column {
         if (ly.l >= L - 1) throw RefError{ST_NULL_NEIGHBOUR};  // self.next_layer is None
         Layer<T>& nl = layers[ly.l + 1];
         if (nl.wf.size() > 1) nb.n2n = nl.wf[1];
-        else if (nl.l < L - 1) nb.n2n = layers[nl.l + 1].wf[0];
+        else if (nl.l < L - 1) nb.n2n = first_front(nl.l + 1);
       } else {
-        if (ly.l < L - 1) nb.n2n = layers[ly.l + 1].wf[0];
+        if (ly.l < L - 1) nb.n2n = first_front(ly.l + 1);
       }
     }
     return nb;
@@ -476,7 +480,7 @@ struct Column {
   // ---- AET: Layer.calc_aet (Layer.py:760-783) -> calc_aet (lgar/aet.py:17-51)
   T calc_aet(double pet, double dt) {
     const Soil<T>& s = layers[0].s;
-    const T& psi_cm = layers[0].wf[0]->psi;
+    const T& psi_cm = first_front(0)->psi;
     T theta_fc = (s.theta_e - s.theta_r) * 0.75 + s.theta_r;  // GlobalParams.py:75
     T wp_head_theta = theta_from_h(T(cfg.wilting_point_psi), s);
     T theta_wp = (theta_fc - wp_head_theta) * 0.5 + wp_head_theta;
@@ -950,12 +954,12 @@ struct Column {
     T h_p = clamp_min_((ponded_depth - precip_sub) * dt, 0.0);
     int lfp = fd->layer_num;
     Layer<T>& fl = layers[lfp];
-    Front<T>* current_front = fl.wf[0];
+    Front<T>* current_front = first_front(lfp);
     Front<T>* next_fd;
     if (fl.wf.size() > 1) next_fd = fl.wf[1];
     else {
       if (lfp >= L - 1) throw RefError{ST_NULL_NEIGHBOUR};
-      next_fd = layers[lfp + 1].wf[0];
+      next_fd = first_front(lfp + 1);
     }
     int nwf = num_fronts();
     T geff(0.0);
@@ -1030,7 +1034,7 @@ struct Column {
       T ponded_water_sub(0.0), percolation_sub(0.0), runoff_sub(0.0), infiltration_sub(0.0), AET_sub(0.0);
       bool create = (val(previous_precip_sub) == 0.0) && (precip_sub > 0.0) && (val(ponded_water) == 0.0);
       fd = calc_wetting_front_free_drainage();
-      bool saturated = val(layers[0].wf[0]->theta) >= val(layers[0].s.theta_e);
+      bool saturated = val(first_front(0)->theta) >= val(layers[0].s.theta_e);
       if (pet_rate > 0.0) AET_sub = calc_aet(pet_rate, dt);
       precip = precip + precip_sub;
       PET = PET + std::fmax(pet_sub, 0.0);

@@ -86,6 +86,13 @@ def cases():
     c["grad_rand_phil_1"] = dict(
         forcing=(PHIL, 4560, 120), grad=G, alpha=al[9], n=nn[9], ksat=ks[9])
     c["grad_phil_dt300_60"] = dict(forcing=(PHIL, 40, 60), grad=G, cfg=dict(subcycle_length=300.0))
+    # columns of the synthetic bench ensemble (lgar_b200.workloads, rank 0, B=16000, T=2560) that reach
+    # Layer.wetting_front_cross_domain_boundary (Layer.py:1010-1053) with percolation != 0, and two that
+    # die with an AttributeError on a missing neighbour (Q10)
+    for col, T_ in ((1620, 620), (573, 800), (449, 1120)):
+        c[f"a16_col{col}"] = dict(ens=(col, T_))
+    for col, T_ in ((10049, 60), (8074, 160)):
+        c[f"null_col{col}"] = dict(ens=(col, T_))
     # full-year known answers (config[0]); no per-step front dump to keep the files small
     c["phil_year"] = dict(forcing=(PHIL, 0, 8760), fronts=False)
     c["bush_year"] = dict(forcing=(BUSH, 0, 8760), cfg=dict(layer_soil_type=(15, 16, 17)),
@@ -97,9 +104,20 @@ def run_case(name):
     from oracle.ref_harness import read_forcing_cm_per_h, run_reference
 
     spec = cases()[name]
-    path, start, count = spec["forcing"]
-    f = read_forcing_cm_per_h(path)
-    f = f[start:] if count is None else f[start:start + count]
+    if "ens" in spec:
+        import lgar_b200  # noqa: F401  (numpy-only workload generator; no GPU needed)
+        from lgar_b200 import workloads
+        col, T_ = spec["ens"]
+        we = workloads.synthetic_sites_ensemble(B=16000, T=2560, sites=128, rank=0)
+        site = int(we.site_index[col])
+        f = we.forcing[site, :T_].copy()
+        spec = dict(spec, alpha=we.alpha[:, col], n=we.n[:, col], ksat=we.ksat[:, col],
+                    cfg=dict(layer_soil_type=(12, 13, 14) if site % 2 == 0 else (15, 16, 17)))
+        path, start, count = f"workloads.synthetic_sites_ensemble(B=16000,T=2560,sites=128,rank=0)/site{site}/col{col}", 0, T_
+    else:
+        path, start, count = spec["forcing"]
+        f = read_forcing_cm_per_h(path)
+        f = f[start:] if count is None else f[start:start + count]
     t0 = time.time()
     r = run_reference(
         f, cfg_kwargs=spec.get("cfg"), alpha=spec.get("alpha"), n=spec.get("n"),

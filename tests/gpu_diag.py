@@ -8,11 +8,23 @@ from lgar_b200 import workloads, ColumnEnsemble, forward_raw
 shapes = [tuple(int(x) for x in a.split("x")) for a in sys.argv[1:]] or [(2048, 256)]
 for B, T in shapes:
     we = workloads.synthetic_sites_ensemble(B=B, T=T, sites=max(1, min(128, B // 32)), rank=0)
+    sl = os.environ.get("LGAR_DIAG_SLICE")
+    if sl:
+        a, cnt = (int(x) for x in sl.split(":"))
+        for k in ("alpha", "n", "ksat", "theta_r", "theta_e", "thickness"):
+            setattr(we, k, np.ascontiguousarray(getattr(we, k)[:, a:a + cnt]))
+        we.site_index = np.ascontiguousarray(we.site_index[a:a + cnt])
+        B = cnt
     ens = ColumnEnsemble(theta_r=we.theta_r, theta_e=we.theta_e, thickness=we.thickness, forcing=we.forcing,
                          site_index=we.site_index)
     torch.cuda.synchronize(); t0 = time.time()
-    res, ws = forward_raw(ens, we.alpha, we.n, we.ksat, outputs=("runoff", "AET"), counters=True)
+    res, ws = forward_raw(ens, we.alpha, we.n, we.ksat, outputs=("runoff", "AET"), counters=True, tile_cycles=True)
     torch.cuda.synchronize(); dt = time.time() - t0
     st = res.status.cpu().numpy(); cr = res.crash_step.cpu().numpy()
     alive = int(np.where(st == 0, T, np.maximum(cr, 0)).sum())
+    if os.environ.get("LGAR_DIAG_SAVE"):
+        os.makedirs("gpurun_out", exist_ok=True)
+        np.savez_compressed(f"gpurun_out/diag_{B}x{T}.npz", sums=res.sums.cpu().numpy(), status=st, crash=cr)
+    tc = res.tile_cycles.cpu().numpy(); top = np.argsort(-tc)[:4]
+    print("  slowest tiles:", [(int(i), round(float(tc[i]) / 1.9e9, 2)) for i in top], "median tile s", round(float(np.median(tc)) / 1.9e9, 3), flush=True)
     print(f"B={B} T={T}: {dt:.3f}s  alive col-steps={alive}  rate={alive/dt:.3g}/s  status hist={np.bincount(st, minlength=9).tolist()} counters={res.counters.cpu().numpy().tolist()}", flush=True)
