@@ -10,7 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "liblgar_b200.so")
 SOURCES = ["lgar_capi.cu"]
-HEADERS = ["lgar_device.cuh", "lgar_forward.cuh", "lgar_backward.cuh", "../../include/lgar_b200.h"]
+HEADERS = ["lgar_device.cuh", "lgar_forward.cuh", "lgar_backward.cuh", "lgar_pow.cuh", "lgar_pow_tables.h",
+           "../../include/lgar_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
