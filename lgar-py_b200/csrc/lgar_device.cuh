@@ -54,69 +54,181 @@ __device__ __forceinline__ void raise(Ctx& c, int code) {
 }
 
 // ------------------------------------------------------------------------------------
-// van Genuchten closures (physics/utils.py).  pow is the inlined table-driven routine of
-// lgar_pow.cuh; the CUDA math library's pow is only the out-of-range fallback.
+// van Genuchten closures (physics/utils.py).
+//
+// Register discipline: the out-of-line functions below are PURE functions of scalar arguments
+// (no Ctx&, no Soil&), so neither the status/counter block nor the soil parameters are forced
+// into local memory by a call.  (With by-reference arguments the 1.2 KB/thread stack thrashed
+// L1 -- the kernel got slower when the shared-memory carve-out was raised -- see DESIGN.md.)
+// The reference's guards (safe_pow / error_check raising ValueError) are evaluated inline by the
+// forceinline wrappers, on the same quantities.
+// pow is the table-driven routine of lgar_pow.cuh; the CUDA math library's pow is only the
+// out-of-range fallback.
 // ------------------------------------------------------------------------------------
 __device__ __noinline__ double pow_slow(double a, double b) { return pow(a, b); }  // specials / range ends
-__device__ __forceinline__ double pow_f64(double a, double b) {
-  double r;
-  if (pow_fast(a, b, &r)) return r;  // lgar_pow.cuh: ~0.50 ulp, ~55 FP64 ops
-  return pow_slow(a, b);
+__device__ __noinline__ double pow_f64(double a, double b) {
+  bool ok;
+  const double r = pow_core(a, b, ok);  // lgar_pow.cuh: ~0.50 ulp
+  return ok ? r : pow_slow(a, b);
+}
+// two INDEPENDENT pows issued interleaved from one basic block (ILP: pow is one long dependent chain)
+__device__ __noinline__ double2 pow_x2(double x0, double y0, double x1, double y1) {
+  bool ok0, ok1;
+  double a = pow_core(x0, y0, ok0);
+  double b = pow_core(x1, y1, ok1);
+  if (!ok0) a = pow_slow(x0, y0);
+  if (!ok1) b = pow_slow(x1, y1);
+  return make_double2(a, b);
 }
 
-// utils.py:12-32 safe_pow: NaN input or negative base raise ValueError
-__device__ __forceinline__ double safe_pow(double base, double e, Ctx& c) {
+// utils.py:12-32 safe_pow guards: NaN input or negative base raise ValueError
+__device__ __forceinline__ void guard_pow(double base, double e, Ctx& c) {
   if (isnan(base) || isnan(e)) raise(c, LGAR_ST_NAN);
   else if (base < 0.0) raise(c, LGAR_ST_NEG_POW);
+}
+__device__ __forceinline__ double safe_pow(double base, double e, Ctx& c) {
+  guard_pow(base, e, c);
   return pow_f64(base, e);
 }
 __device__ __forceinline__ double error_check(double r, Ctx& c) {  // utils.py:177-185
   if (isnan(r)) raise(c, LGAR_ST_NAN);
   return r;
 }
-// utils.py:35-51
+
+// ---- pure cores -----------------------------------------------------------------------
+// utils.py:35-51   theta = theta_r + (theta_e - theta_r) / (1 + (alpha h)^n)^m
+__device__ __noinline__ double theta_h_core(double h, double alpha, double n, double m, double the, double thr) {
+  const double outer = pow_f64(1.0 + pow_f64(alpha * h, n), m);
+  return (1.0 / outer * (the - thr)) + thr;
+}
+__device__ __noinline__ double2 theta_h_core_x2(double h0, double al0, double n0, double m0, double the0, double thr0,
+                                                double h1, double al1, double n1, double m1, double the1, double thr1) {
+  const double2 p = pow_x2(al0 * h0, n0, al1 * h1, n1);
+  const double2 q = pow_x2(1.0 + p.x, m0, 1.0 + p.y, m1);
+  return make_double2((1.0 / q.x * (the0 - thr0)) + thr0, (1.0 / q.y * (the1 - thr1)) + thr1);
+}
+// utils.py:159-174   h = (Se^(-1/m) - 1)^(1/n) / alpha ; returns NaN-coded guard via *bad
+__device__ __noinline__ double h_se_core(double se, double alpha, double ninv_m, double inv_n, int* bad) {
+  double base = pow_f64(se, ninv_m) - 1.0;
+  if (fabs(base) <= 1e-8) base = base + 1e-12;  // torch.isclose(base, 0, 1e-12) == |base| <= 1e-8 (Q2)
+  *bad = isnan(base) ? LGAR_ST_NAN : (base < 0.0 ? LGAR_ST_NEG_POW : 0);
+  return 1.0 / alpha * pow_f64(base, inv_n);
+}
+// utils.py:134-156   K = Ks sqrt(Se) (1 - (1 - Se^(1/m))^m)^2 ; pow(x, 2) == x*x bit-for-bit in glibc
+__device__ __noinline__ double k_se_core(double se, double ksat, double m, double inv_m, int* bad) {
+  double base = 1.0 - pow_f64(se, inv_m);
+  if (fabs(base) <= 1e-8) base = base + 1e-12;
+  int b = isnan(base) ? LGAR_ST_NAN : (base < 0.0 ? LGAR_ST_NEG_POW : 0);
+  const double t = 1.0 - pow_f64(base, m);
+  if (!b) b = isnan(t) ? LGAR_ST_NAN : (t < 0.0 ? LGAR_ST_NEG_POW : 0);
+  *bad = b;
+  return ksat * sqrt(se) * (t * t);
+}
+// psi = h(Se) and K = K(Se) for the same Se: two independent chains interleaved
+__device__ __noinline__ double2 psi_k_core(double se, double alpha, double ninv_m, double inv_n, double ksat, double m,
+                                           double inv_m, int* bad) {
+  const double2 p = pow_x2(se, ninv_m, se, inv_m);
+  double bh = p.x - 1.0;
+  if (fabs(bh) <= 1e-8) bh = bh + 1e-12;
+  double bk = 1.0 - p.y;
+  if (fabs(bk) <= 1e-8) bk = bk + 1e-12;
+  int b = (isnan(bh) || isnan(bk)) ? LGAR_ST_NAN : ((bh < 0.0 || bk < 0.0) ? LGAR_ST_NEG_POW : 0);
+  const double2 o = pow_x2(bh, inv_n, bk, m);
+  const double t = 1.0 - o.y;
+  if (!b) b = isnan(t) ? LGAR_ST_NAN : (t < 0.0 ? LGAR_ST_NEG_POW : 0);
+  *bad = b;
+  return make_double2(1.0 / alpha * o.x, ksat * sqrt(se) * (t * t));
+}
+// two h(Se) with the same soil (Geff end points)
+__device__ __noinline__ double2 h_se_core_x2(double se0, double se1, double alpha, double ninv_m, double inv_n, int* bad) {
+  const double2 p = pow_x2(se0, ninv_m, se1, ninv_m);
+  double b0 = p.x - 1.0, b1 = p.y - 1.0;
+  if (fabs(b0) <= 1e-8) b0 = b0 + 1e-12;
+  if (fabs(b1) <= 1e-8) b1 = b1 + 1e-12;
+  *bad = (isnan(b0) || isnan(b1)) ? LGAR_ST_NAN : ((b0 < 0.0 || b1 < 0.0) ? LGAR_ST_NEG_POW : 0);
+  const double2 o = pow_x2(b0, inv_n, b1, inv_n);
+  return make_double2(1.0 / alpha * o.x, 1.0 / alpha * o.y);
+}
+// K(Se(h)) at two trapezoid nodes of one Geff request (green_ampt.py:75-81): se_from_h (utils.py:115-131,
+// constant 1.0 for |h| < 0.1, Q12) then k_from_se
+__device__ __noinline__ double2 k_nodes_core_x2(double h0, double h1, double alpha, double n, double m, double inv_m,
+                                                double ksat, int* bad) {
+  const bool w0 = fabs(h0) < 1.0e-01, w1 = fabs(h1) < 1.0e-01;
+  const double a0 = w0 ? 1.0 : alpha * h0, a1 = w1 ? 1.0 : alpha * h1;
+  int b = (isnan(a0) || isnan(a1)) ? LGAR_ST_NAN : ((a0 < 0.0 || a1 < 0.0) ? LGAR_ST_NEG_POW : 0);
+  const double2 p = pow_x2(a0, n, a1, n);
+  const double2 d = pow_x2(1.0 + p.x, m, 1.0 + p.y, m);
+  double se0 = 1.0 / d.x, se1 = 1.0 / d.y;
+  if (!b && (isnan(se0) || isnan(se1))) b = LGAR_ST_NAN;
+  if (w0) se0 = 1.0;
+  if (w1) se1 = 1.0;
+  const double2 sp = pow_x2(se0, inv_m, se1, inv_m);
+  double b0 = 1.0 - sp.x, b1 = 1.0 - sp.y;
+  if (fabs(b0) <= 1e-8) b0 = b0 + 1e-12;
+  if (fabs(b1) <= 1e-8) b1 = b1 + 1e-12;
+  if (!b) b = (isnan(b0) || isnan(b1)) ? LGAR_ST_NAN : ((b0 < 0.0 || b1 < 0.0) ? LGAR_ST_NEG_POW : 0);
+  const double2 o = pow_x2(b0, m, b1, m);
+  const double t0 = 1.0 - o.x, t1 = 1.0 - o.y;
+  if (!b) b = (isnan(t0) || isnan(t1)) ? LGAR_ST_NAN : ((t0 < 0.0 || t1 < 0.0) ? LGAR_ST_NEG_POW : 0);
+  *bad = b;
+  return make_double2(ksat * sqrt(se0) * (t0 * t0), ksat * sqrt(se1) * (t1 * t1));
+}
+
+// ---- guarded wrappers (inline) ----------------------------------------------------------
 __device__ __forceinline__ double theta_from_h(double h, const Soil& s, Ctx& c) {
   c.cnt[C_THETA_H]++;
-  double alpha_pow = safe_pow(s.alpha * h, s.n, c);
-  double outer = safe_pow(1.0 + alpha_pow, s.m, c);
-  double r = (1.0 / outer * (s.the - s.thr)) + s.thr;
-  return error_check(r, c);
+  guard_pow(s.alpha * h, s.n, c);
+  return error_check(theta_h_core(h, s.alpha, s.n, s.m, s.the, s.thr), c);
+}
+// two theta_from_h; `both` == false: only the first result is meaningful
+__device__ __forceinline__ double2 theta_from_h_x2(double h0, const Soil& s0, double h1, const Soil& s1, bool both, Ctx& c) {
+  c.cnt[C_THETA_H] += both ? 2 : 1;
+  guard_pow(s0.alpha * h0, s0.n, c);
+  if (both) guard_pow(s1.alpha * h1, s1.n, c);
+  const double2 r = theta_h_core_x2(h0, s0.alpha, s0.n, s0.m, s0.the, s0.thr, both ? h1 : 1.0, s1.alpha, s1.n, s1.m,
+                                    s1.the, s1.thr);
+  if (isnan(r.x) || (both && isnan(r.y))) raise(c, LGAR_ST_NAN);
+  return r;
 }
 // utils.py:102-112
 __device__ __forceinline__ double se_from_theta(double theta, const Soil& s, Ctx& c) {
   return error_check((theta - s.thr) / (s.the - s.thr), c);
 }
-// utils.py:115-131 (constant 1.0 for |h| < 0.1, Q12)
-__device__ __forceinline__ double se_from_h(double h, const Soil& s, Ctx& c) {
-  c.cnt[C_SE_H]++;
-  if (fabs(h) < 1.0e-01) return 1.0;
-  double internal = safe_pow(s.alpha * h, s.n, c);
-  double r = 1.0 / safe_pow(1.0 + internal, s.m, c);
-  return error_check(r, c);
-}
-// utils.py:134-156.  torch.isclose(base, 0, 1e-12) == |base| <= 1e-8 (Q2); pow(x, 2) == x*x
-// bit-for-bit in glibc (checked over 5e6 samples).
 __device__ __forceinline__ double k_from_se(double se, double ksat, double m, double inv_m, Ctx& c) {
   c.cnt[C_K_SE]++;
-  double se_pow = safe_pow(se, inv_m, c);
-  double base = 1.0 - se_pow;
-  if (fabs(base) <= 1e-8) base = base + 1e-12;
-  double outside = safe_pow(base, m, c);
-  double t = 1.0 - outside;
-  if (isnan(t)) raise(c, LGAR_ST_NAN);
-  else if (t < 0.0) raise(c, LGAR_ST_NEG_POW);
-  double r = ksat * sqrt(se) * (t * t);
+  guard_pow(se, inv_m, c);
+  int bad;
+  const double r = k_se_core(se, ksat, m, inv_m, &bad);
+  if (bad) raise(c, bad);
   return error_check(r, c);
 }
-// utils.py:159-174
 __device__ __forceinline__ double h_from_se(double se, const Soil& s, Ctx& c) {
   c.cnt[C_H_SE]++;
-  double se_pow = safe_pow(se, s.ninv_m, c);
-  double base = se_pow - 1.0;
-  if (fabs(base) <= 1e-8) base = base + 1e-12;
-  double outside = safe_pow(base, s.inv_n, c);
-  double r = 1.0 / s.alpha * outside;
+  guard_pow(se, s.ninv_m, c);
+  int bad;
+  const double r = h_se_core(se, s.alpha, s.ninv_m, s.inv_n, &bad);
+  if (bad) raise(c, bad);
   return error_check(r, c);
+}
+__device__ __forceinline__ double2 psi_k_from_se(double se, const Soil& s, Ctx& c) {
+  c.cnt[C_H_SE]++;
+  c.cnt[C_K_SE]++;
+  guard_pow(se, s.ninv_m, c);
+  int bad;
+  const double2 r = psi_k_core(se, s.alpha, s.ninv_m, s.inv_n, s.ksat, s.m, s.inv_m, &bad);
+  if (bad) raise(c, bad);
+  if (isnan(r.x) || isnan(r.y)) raise(c, LGAR_ST_NAN);
+  return r;
+}
+__device__ __forceinline__ double2 h_from_se_x2(double se0, double se1, const Soil& s, Ctx& c) {
+  c.cnt[C_H_SE] += 2;
+  guard_pow(se0, s.ninv_m, c);
+  guard_pow(se1, s.ninv_m, c);
+  int bad;
+  const double2 r = h_se_core_x2(se0, se1, s.alpha, s.ninv_m, s.inv_n, &bad);
+  if (bad) raise(c, bad);
+  if (isnan(r.x) || isnan(r.y)) raise(c, LGAR_ST_NAN);
+  return r;
 }
 
 // ------------------------------------------------------------------------------------
@@ -181,7 +293,7 @@ __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync
 //            nodes j, j+32, j+64, ...
 //   stage C (requesting lane): geff = sum_i (K_{i-1} + K_i) * (dh / 2) in the reference's order.
 // ------------------------------------------------------------------------------------
-__device__ __noinline__ double geff_warp(bool need, double theta_1, double theta_2, const Soil& s, int nint,
+__device__ __forceinline__ double geff_warp(bool need, double theta_1, double theta_2, const Soil& s, int nint,
                                          double* nodebuf, Ctx& c) {
   const int lane = threadIdx.x & 31;
   double h_i = 0.0, dh = 0.0, k0 = 0.0;
@@ -189,8 +301,9 @@ __device__ __noinline__ double geff_warp(bool need, double theta_1, double theta
     c.cnt[C_GEFF]++;
     double se_i = se_from_theta(theta_1, s, c);
     double se_f = se_from_theta(theta_2, s, c);
-    h_i = h_from_se(se_i, s, c);
-    double h_f = h_from_se(se_f, s, c);
+    const double2 hh = h_from_se_x2(se_i, se_f, s, c);
+    h_i = hh.x;
+    const double h_f = hh.y;
     // "Checkpoint" calls green_ampt.py:61-63: results unused, only their guards can matter
     if (fabs(h_i) >= 0.1 && s.alpha * h_i < 0.0) raise(c, LGAR_ST_NEG_POW);
     if (fabs(h_f) >= 0.1 && s.alpha * h_f < 0.0) raise(c, LGAR_ST_NEG_POW);
@@ -212,29 +325,47 @@ __device__ __noinline__ double geff_warp(bool need, double theta_1, double theta
     const double qh = shfl_d(h_i, src);
     const double qdh = shfl_d(dh, src);
     const double qk0 = shfl_d(k0, src);
-    Ctx cc;  // guards raised while evaluating nodes are reported to the requesting lane
-    cc.st = 0;
-    double h = qh;
-    int k = 0;
-    for (int target = lane; target <= nint; target += 32) {
-      while (k < target) {  // h2 = h2 + dh, k times
-        h = h + qdh;
-        k++;
+    int cc_st = 0;  // guards raised while evaluating nodes are reported to the requesting lane
+    // node t has h = h_i + dh + dh + ... (t rounded additions): advance_rounded() gives exactly that
+    // value without walking the chain; lanes take nodes lane, lane+32, lane+64, lane+96 in two pairs
+    double hn[4];
+    {
+      double h = qh;
+      int done = 0;
+#pragma unroll
+      for (int rdx = 0; rdx < 4; rdx++) {
+        const int target = lane + 32 * rdx;
+        if (target <= nint && target > done) {
+          const double h0 = h;
+          h = advance_rounded(h0, qdh, target - done);
+          if (!(h > 0.0)) {  // outside the positive range of the exact jump: walk the chain
+            h = h0;
+            for (int w = done; w < target; w++) h = h + qdh;
+          }
+          done = target;
+        }
+        hn[rdx] = h;
       }
-      double kk;
-      if (target == 0) {
-        kk = qk0;
-      } else {
-        double se2 = se_from_h(h, q, cc);
-        kk = k_from_se(se2, q.ksat, q.m, q.inv_m, cc);
-      }
-      nodebuf[target] = kk;
     }
-    unsigned bad = __ballot_sync(0xffffffffu, cc.st != 0);
+#pragma unroll
+    for (int pr = 0; pr < 2; pr++) {
+      const int ta = lane + 64 * pr, tb = ta + 32;
+      if (ta <= nint) {
+        const bool both = tb <= nint;
+        int bad;
+        const double2 kk = k_nodes_core_x2(hn[2 * pr], both ? hn[2 * pr + 1] : hn[2 * pr], q.alpha, q.n, q.m, q.inv_m,
+                                           q.ksat, &bad);
+        if (bad == 0 && (isnan(kk.x) || isnan(kk.y))) bad = LGAR_ST_NAN;
+        if (bad && cc_st == 0) cc_st = bad;
+        nodebuf[ta] = (ta == 0) ? qk0 : kk.x;
+        if (both) nodebuf[tb] = kk.y;
+      }
+    }
+    unsigned badmask = __ballot_sync(0xffffffffu, cc_st != 0);
     int st_any = 0;
-    if (bad) {
-      int b = __ffs(bad) - 1;  // lowest node raises first in the sequential reference
-      st_any = __shfl_sync(0xffffffffu, cc.st, b);
+    if (badmask) {
+      int b = __ffs(badmask) - 1;  // lowest node raises first in the sequential reference
+      st_any = __shfl_sync(0xffffffffu, cc_st, b);
     }
     __syncwarp();
     if (lane == src) {
@@ -560,21 +691,18 @@ struct Column {
           if (k < nup) {
             const Soil& sk = soil[k];
             if (kind == K_INLAYER_DEEP) {
-              double theta_old = theta_from_h(psi_old, sk, c);
-              double theta_below_old = theta_from_h(psi_below_old, sk, c);
-              double local_delta_old = theta_old - theta_below_old;
+              const double2 ob = theta_from_h_x2(psi_old, sk, psi_below_old, sk, true, c);
+              double local_delta_old = ob.x - ob.y;
               double layer_thickness = cum[k] - 0.0;  // sic (Q5): cumulative thickness
               prior_mass = prior_mass + (layer_thickness * local_delta_old);
-              double theta = theta_from_h(psi_cm, sk, c);
-              double theta_below = theta_from_h(psi_below, sk, c);
-              new_mass = new_mass + (layer_thickness * (theta - theta_below));
-              dth[k] = theta_below;
+              const double2 nb2 = theta_from_h_x2(psi_cm, sk, psi_below, sk, true, c);
+              new_mass = new_mass + (layer_thickness * (nb2.x - nb2.y));
+              dth[k] = nb2.y;
               dtk[k] = layer_thickness;
             } else {  // K_BASE
-              double theta_old = theta_from_h(psi_old, sk, c);
-              prior_mass = prior_mass + thick[k] * (theta_old - 0.0);
-              double theta = theta_from_h(psi_cm, sk, c);
-              new_mass = new_mass + thick[k] * (theta - 0.0);
+              const double2 on = theta_from_h_x2(psi_old, sk, psi_cm, sk, true, c);
+              prior_mass = prior_mass + thick[k] * (on.x - 0.0);
+              new_mass = new_mass + thick[k] * (on.y - 0.0);
               dth[k] = 0.0;
               dtk[k] = thick[k];
             }
@@ -585,7 +713,9 @@ struct Column {
 
       // ---- P2: batched theta_mass_balance
       const double tol = 1e-12;
-      const Soil own = soil[lyr];
+      const Soil own = soil[lyr];  // hoisted into registers for the iteration loop
+      const Soil up0 = soil[0];
+      const Soil up1 = soil[(MAXL > 2) ? 1 : 0];
       double delta_mass = fabs(new_mass - prior_mass);
       double theta = 0.0;
       const bool wants = mine && (kind == K_DEEPEST || kind >= K_INLAYER_DEEP) && (c.st == 0);
@@ -644,10 +774,17 @@ struct Column {
             Ctx cc;  // guards raised by a rejected probe must not kill the column
             cc.st = 0;
             cc.cnt[C_THETA_H] = 0;
-            const double th = theta_from_h(psi_try, own, cc);
+            // own layer + first upper layer evaluated as an interleaved pair; further upper layers singly
+            const double2 t01 = theta_from_h_x2(psi_try, own, psi_try, up0, nup > 0, cc);
+            const double th = t01.x;
             double mass_layers = 0.0 + (own_dtk * (th - own_dth));
+            if (nup > 0) mass_layers = mass_layers + dtk[0] * (t01.y - dth[0]);
+            if (nup > 1) {
+              double theta_layer = theta_from_h(psi_try, up1, cc);
+              mass_layers = mass_layers + dtk[1] * (theta_layer - dth[1]);
+            }
 #pragma unroll
-            for (int k = 0; k < MAXL - 1; k++) {
+            for (int k = 2; k < MAXL - 1; k++) {
               if (k < nup) {
                 double theta_layer = theta_from_h(psi_try, soil[k], cc);
                 mass_layers = mass_layers + dtk[k] * (theta_layer - dth[k]);
@@ -991,8 +1128,9 @@ struct Column {
         }
         const Soil& s = soil[l];
         double se = se_from_theta(f(F_THETA, i), s, c);
-        f(F_PSI, i) = h_from_se(se, s, c);
-        f(F_K, i) = k_from_se(se, s.ksat, s.m, s.inv_m, c);
+        const double2 pk = psi_k_from_se(se, s, c);
+        f(F_PSI, i) = pk.x;
+        f(F_K, i) = pk.y;
       }
     }
   }

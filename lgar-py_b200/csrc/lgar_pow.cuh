@@ -67,11 +67,13 @@ LGAR_HD double pow_fma(double a, double b, double c) {
 #endif
 }
 
-// returns true and sets *out on the fast path; false -> caller must use the library pow
-LGAR_HD bool pow_fast(double x, double y, double* out) {
+// Branch-free core.  Returns the fast-path value and sets ok = false when the arguments are outside
+// the fast path (the caller then uses the library pow).  Being branch-free, two or more calls in one
+// basic block are interleaved by the scheduler (ILP): see pow_x2 in lgar_device.cuh.
+LGAR_HD double pow_core(double x, double y, bool& ok) {
   const uint64_t ix = pow_bits(x);
   // x must be a positive normal number
-  if (ix - 0x0010000000000000ULL >= 0x7ff0000000000000ULL - 0x0010000000000000ULL) return false;
+  const bool x_ok = (ix - 0x0010000000000000ULL) < (0x7ff0000000000000ULL - 0x0010000000000000ULL);
   // ---- log(x) = hi + lo
   const uint64_t tmp = ix - LGAR_POW_OFF;
   const int i = (int)((tmp >> 45) & (LGAR_POW_N - 1));
@@ -117,17 +119,13 @@ LGAR_HD bool pow_fast(double x, double y, double* out) {
   // ---- ehi + elo = y * log(x)
   const double ehi = y * lhi;
   const double elo = pow_fma(y, llo, pow_fma(y, lhi, -ehi));
-  // result must stay well inside the normal range: |ehi| < 700 and not so tiny that 1 + e rounds oddly
+  // result must stay well inside the normal range (also rejects NaN / inf in y)
   const double aeh = ehi < 0.0 ? -ehi : ehi;
-  if (!(aeh < 700.0)) return false;  // also catches NaN / inf in y
-  if (aeh < 0x1p-60) {
-    *out = 1.0 + ehi;  // |y log x| tiny: pow = 1 + y log x to well below half an ulp
-    return true;
-  }
+  ok = x_ok && (aeh < 700.0);
   // ---- exp(ehi + elo)
   const double zz = ehi * LGAR_INVLN2N;
   const double kf = (zz + 0x1.8p52) - 0x1.8p52;  // rint(zz), |zz| < 2^17
-  const int64_t ki = (int64_t)kf;
+  const int64_t ki = ok ? (int64_t)kf : 0;
   double rr = pow_fma(kf, -LGAR_LN2N_HI, ehi);   // exact: kf*LN2N_HI has <= 52 bits
   rr = pow_fma(kf, -LGAR_LN2N_LO, rr);
   rr = rr + elo;
@@ -145,8 +143,16 @@ LGAR_HD bool pow_fast(double x, double y, double* out) {
   double e4 = pow_fma(rr, LGAR_EXP_C5, LGAR_EXP_C4);
   e4 = pow_fma(rr2, LGAR_EXP_C6, e4);
   const double tmp2 = tailj + (rr + (rr2 * e2 + (rr2 * rr2) * e4));
-  *out = pow_fma(scale, tmp2, scale);
-  return true;
+  const double res = pow_fma(scale, tmp2, scale);
+  // |y log x| tiny: pow = 1 + y log x to well below half an ulp
+  return (aeh < 0x1p-60) ? (1.0 + ehi) : res;
+}
+
+// returns true and sets *out on the fast path; false -> caller must use the library pow
+LGAR_HD bool pow_fast(double x, double y, double* out) {
+  bool ok;
+  *out = pow_core(x, y, ok);
+  return ok;
 }
 
 }  // namespace lgar
