@@ -24,6 +24,8 @@
 #include <cuda_runtime.h>
 #include "../../include/lgar_b200.h"
 #include "lgar_pow.cuh"
+#include "lgar_var.cuh"
+#include <type_traits>
 
 namespace lgar {
 
@@ -389,25 +391,267 @@ __device__ __forceinline__ double geff_warp(bool need, double theta_1, double th
 }
 
 // ------------------------------------------------------------------------------------
-// Column: per-thread view of the front list in shared memory + scalar state in registers
+// Scalar-generic layer: R = double (forward kernel) or R = Var (taped pass of the reverse kernel).
 // ------------------------------------------------------------------------------------
-template <int FM>
+template <class R>
+struct SoilT;
+template <>
+struct SoilT<double> : Soil {
+  __device__ __forceinline__ double ksatR() const { return ksat; }
+};
+template <>
+struct SoilT<Var> : Soil {
+  int id_alpha, id_n, id_m, id_ksat;  // tape ids of the differentiable parameters (m = 1 - 1/n is derived on tape)
+  __device__ __forceinline__ Var ksatR() const { return Var(ksat, id_ksat); }
+};
+
+// ---- theta(h)
+__device__ __forceinline__ double thetaR(double h, const SoilT<double>& s, Ctx& c) { return theta_from_h(h, s, c); }
+__device__ __forceinline__ Var thetaR(const Var& h, const SoilT<Var>& s, Ctx& c) {
+  const double v = theta_from_h(h.v, s, c);
+  // x = alpha h; ap = x^n; u = 1 + ap; o = u^m; theta = (the - thr)/o + thr
+  const double x = s.alpha * h.v;
+  const double ap = pow_f64(x, s.n);
+  const double u = 1.0 + ap;
+  const double o = pow_f64(u, s.m);
+  const double dth_do = -(s.the - s.thr) / (o * o);
+  const double do_du = s.m * o / u;
+  const double dap_dx = (x == 0.0) ? 0.0 : s.n * ap / x;
+  const double dap_dn = (x == 0.0) ? 0.0 : ap * log(x);
+  const double g = dth_do * do_du;
+  const int ids[4] = {h.id, s.id_alpha, s.id_n, s.id_m};
+  const double d[4] = {g * dap_dx * s.alpha, g * dap_dx * h.v, g * dap_dn, dth_do * o * log(u)};
+  return tape_record_n(v, 4, ids, d);
+}
+// ---- Se(theta)
+__device__ __forceinline__ double se_thetaR(double theta, const SoilT<double>& s, Ctx& c) { return se_from_theta(theta, s, c); }
+__device__ __forceinline__ Var se_thetaR(const Var& theta, const SoilT<Var>& s, Ctx& c) {
+  return tape_record(se_from_theta(theta.v, s, c), theta.id, 1.0 / (s.the - s.thr), -1, 0.0);
+}
+// ---- h(Se) partials: sp = se^(-1/m); base = sp - 1; op = base^(1/n); h = op / alpha
+__device__ __forceinline__ void h_se_partials(double se, const Soil& s, double hval, double* d_se, double* d_alpha,
+                                              double* d_n, double* d_m) {
+  const double sp = pow_f64(se, s.ninv_m);
+  double base = sp - 1.0;
+  if (fabs(base) <= 1e-8) base = base + 1e-12;
+  const double op = hval * s.alpha;
+  const double dop_dbase = s.inv_n * op / base;
+  const double dsp_dse = (se == 0.0) ? 0.0 : s.ninv_m * sp / se;
+  const double dsp_dm = (se == 0.0) ? 0.0 : sp * log(se) * (s.inv_m * s.inv_m);  // d(-1/m)/dm = 1/m^2
+  const double dop_dn = (base == 0.0) ? 0.0 : op * log(base) * (-(s.inv_n * s.inv_n));
+  *d_se = dop_dbase * dsp_dse / s.alpha;
+  *d_alpha = -hval / s.alpha;
+  *d_n = dop_dn / s.alpha;
+  *d_m = dop_dbase * dsp_dm / s.alpha;
+}
+__device__ __forceinline__ double h_seR(double se, const SoilT<double>& s, Ctx& c) { return h_from_se(se, s, c); }
+__device__ __forceinline__ Var h_seR(const Var& se, const SoilT<Var>& s, Ctx& c) {
+  const double v = h_from_se(se.v, s, c);
+  double d_se, d_a, d_n, d_m;
+  h_se_partials(se.v, s, v, &d_se, &d_a, &d_n, &d_m);
+  const int ids[4] = {se.id, s.id_alpha, s.id_n, s.id_m};
+  const double d[4] = {d_se, d_a, d_n, d_m};
+  return tape_record_n(v, 4, ids, d);
+}
+// ---- K(Se) partials: sp = se^(1/m); base = 1 - sp; op = base^m; t = 1 - op; K = ksat sqrt(se) t^2
+__device__ __forceinline__ void k_se_partials(double se, double ksat, double m, double inv_m, double* d_se, double* d_ksat,
+                                              double* d_m) {
+  const double sp = pow_f64(se, inv_m);
+  double base = 1.0 - sp;
+  if (fabs(base) <= 1e-8) base = base + 1e-12;
+  const double op = pow_f64(base, m);
+  const double t = 1.0 - op;
+  const double rs = sqrt(se);
+  const double sp_over = (se == 0.0) ? 0.0 : sp / se;
+  // -dop/dse = op sp / (base se);  dop/dm = op ln(base) + op sp ln(se) / (base m)
+  const double ndop_dse = op * sp_over / base;
+  const double lnse = (se == 0.0) ? 0.0 : log(se);
+  const double dop_dm = op * log(base) + op * sp * lnse / (base * m);
+  *d_se = ksat * ((rs == 0.0 ? 0.0 : t * t / (2.0 * rs)) + 2.0 * t * rs * ndop_dse);
+  *d_ksat = rs * (t * t);
+  *d_m = ksat * rs * 2.0 * t * (-dop_dm);
+}
+__device__ __forceinline__ double k_seR(double se, const SoilT<double>& s, Ctx& c) {
+  return k_from_se(se, s.ksat, s.m, s.inv_m, c);
+}
+__device__ __forceinline__ Var k_seR(const Var& se, const SoilT<Var>& s, Ctx& c) {
+  const double v = k_from_se(se.v, s.ksat, s.m, s.inv_m, c);
+  double d_se, d_k, d_m;
+  k_se_partials(se.v, s.ksat, s.m, s.inv_m, &d_se, &d_k, &d_m);
+  const int ids[3] = {se.id, s.id_ksat, s.id_m};
+  const double d[3] = {d_se, d_k, d_m};
+  return tape_record_n(v, 3, ids, d);
+}
+// ---- psi and K from the same Se
+template <class R>
+struct Pair {
+  R x, y;
+};
+__device__ __forceinline__ Pair<double> psi_kR(double se, const SoilT<double>& s, Ctx& c) {
+  const double2 r = psi_k_from_se(se, s, c);
+  Pair<double> p;
+  p.x = r.x;
+  p.y = r.y;
+  return p;
+}
+__device__ __forceinline__ Pair<Var> psi_kR(const Var& se, const SoilT<Var>& s, Ctx& c) {
+  const double2 r = psi_k_from_se(se.v, s, c);  // same values as the forward kernel
+  double d_se, d_a, d_n, d_m, e_se, e_k, e_m;
+  h_se_partials(se.v, s, r.x, &d_se, &d_a, &d_n, &d_m);
+  k_se_partials(se.v, s.ksat, s.m, s.inv_m, &e_se, &e_k, &e_m);
+  const int ids[4] = {se.id, s.id_alpha, s.id_n, s.id_m};
+  const double d[4] = {d_se, d_a, d_n, d_m};
+  const int ids2[3] = {se.id, s.id_ksat, s.id_m};
+  const double d2[3] = {e_se, e_k, e_m};
+  Pair<Var> p;
+  p.x = tape_record_n(r.x, 4, ids, d);
+  p.y = tape_record_n(r.y, 3, ids2, d2);
+  return p;
+}
+
+// ---- Geff: value from the forward routine (bit-identical), partials cooperatively (lanes = nodes).
+//      G = dh sum_k w_k K_k, geff = |G / ksat|; K_k = K(Se(h_k)), h_k = h_i + k dh, node 0 uses K(Se_i).
+//      d geff / d ksat = 0 (K is proportional to ksat).
+__device__ __forceinline__ double geff_warpR(bool need, double theta_1, double theta_2, const SoilT<double>& s, int nint,
+                                            double* nodebuf, Ctx& c) {
+  return geff_warp(need, theta_1, theta_2, s, nint, nodebuf, c);
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+__device__ Var geff_warpR(bool need, const Var& theta_1, const Var& theta_2, const SoilT<Var>& s, int nint,
+                          double* nodebuf, Ctx& c) {
+  const double value = geff_warp(need, theta_1.v, theta_2.v, s, nint, nodebuf, c);
+  const int lane = threadIdx.x & 31;
+  // request scalars (same expressions as stage A of geff_warp)
+  double se_i = 1.0, se_f = 1.0, h_i = 0.0, h_f = 0.0;
+  Ctx cz = c;  // guards were already evaluated by the value pass
+  if (need) {
+    se_i = se_from_theta(theta_1.v, s, cz);
+    se_f = se_from_theta(theta_2.v, s, cz);
+    const double2 hh = h_from_se_x2(se_i, se_f, s, cz);
+    h_i = hh.x;
+    h_f = hh.y;
+  }
+  unsigned mask = __ballot_sync(0xffffffffu, need);
+  Var result(value);
+  while (mask) {
+    const int src = __ffs(mask) - 1;
+    mask &= mask - 1;
+    Soil q;
+    q.alpha = shfl_d(s.alpha, src);
+    q.n = shfl_d(s.n, src);
+    q.m = shfl_d(s.m, src);
+    q.inv_m = shfl_d(s.inv_m, src);
+    q.ksat = shfl_d(s.ksat, src);
+    const double qhi = shfl_d(h_i, src), qhf = shfl_d(h_f, src), qsei = shfl_d(se_i, src);
+    const double qdh = (qhf - qhi) / (double)nint;
+    double S = 0.0, Ahi = 0.0, Ahf = 0.0, Ca = 0.0, Cn = 0.0, Cm = 0.0, Csei = 0.0;
+    for (int k = lane; k <= nint; k += 32) {
+      const double w = (k == 0 || k == nint) ? 0.5 : 1.0;
+      double se, dse_dh = 0.0, dse_da = 0.0, dse_dn = 0.0, dse_dm = 0.0;
+      if (k == 0) {
+        se = qsei;
+      } else {
+        const double h = qhi + (double)k * qdh;  // derivative weights only: no need for the rounded chain
+        if (fabs(h) < 0.1) {
+          se = 1.0;
+        } else {
+          const double x = q.alpha * h;
+          const double ap = pow_f64(x, q.n);
+          const double u = 1.0 + ap;
+          se = 1.0 / pow_f64(u, q.m);
+          const double dse_du = -q.m * se / u;
+          const double dap_dx = (x == 0.0) ? 0.0 : q.n * ap / x;
+          dse_dh = dse_du * dap_dx * q.alpha;
+          dse_da = dse_du * dap_dx * h;
+          dse_dn = (x == 0.0) ? 0.0 : dse_du * ap * log(x);
+          dse_dm = -se * log(u);
+        }
+      }
+      double dk_se, dk_ks, dk_m;
+      k_se_partials(se, q.ksat, q.m, q.inv_m, &dk_se, &dk_ks, &dk_m);
+      const double kk = dk_ks * q.ksat;  // K itself
+      S += w * kk;
+      const double frac = (double)k / (double)nint;
+      if (k == 0) {
+        Csei += w * dk_se;
+      } else {
+        Ahi += w * dk_se * dse_dh * (1.0 - frac);
+        Ahf += w * dk_se * dse_dh * frac;
+        Ca += w * dk_se * dse_da;
+        Cn += w * dk_se * dse_dn;
+      }
+      Cm += w * (dk_se * dse_dm + dk_m);
+    }
+    S = warp_sum(S); Ahi = warp_sum(Ahi); Ahf = warp_sum(Ahf); Ca = warp_sum(Ca); Cn = warp_sum(Cn);
+    Cm = warp_sum(Cm); Csei = warp_sum(Csei);
+    if (lane == src) {
+      const double G = qdh * S;
+      const double sg = (G / q.ksat > 0.0) ? 1.0 : ((G / q.ksat < 0.0) ? -1.0 : 0.0);
+      const double f = sg / q.ksat;
+      const double dG_dhi = -S / (double)nint + qdh * Ahi;
+      const double dG_dhf = S / (double)nint + qdh * Ahf;
+      double hi_se, hi_a, hi_n, hi_m, hf_se, hf_a, hf_n, hf_m;
+      h_se_partials(se_i, s, h_i, &hi_se, &hi_a, &hi_n, &hi_m);
+      h_se_partials(se_f, s, h_f, &hf_se, &hf_a, &hf_n, &hf_m);
+      const double inv_span = 1.0 / (s.the - s.thr);
+      const int ids[5] = {theta_1.id, theta_2.id, s.id_alpha, s.id_n, s.id_m};
+      const double d[5] = {f * (dG_dhi * hi_se + qdh * Csei) * inv_span, f * (dG_dhf * hf_se) * inv_span,
+                           f * (qdh * Ca + dG_dhi * hi_a + dG_dhf * hf_a), f * (qdh * Cn + dG_dhi * hi_n + dG_dhf * hf_n),
+                           f * (qdh * Cm + dG_dhi * hi_m + dG_dhf * hf_m)};
+      result = tape_record_n(value, 5, ids, d);
+    }
+  }
+  return result;
+}
+
+// ------------------------------------------------------------------------------------
+// Column: per-thread view of the front list in shared memory + scalar state in registers.
+// R = double: forward kernel.  R = Var: taped pass (values in the same shared-memory array, tape
+// ids of the five fields in a parallel int array).
+// ------------------------------------------------------------------------------------
+template <int FM, class R>
 struct Column {
+  static constexpr bool TAPED = !std::is_same<R, double>::value;
   double* fb;        // this thread's slot in the field array
+  int* ib;           // this thread's slot in the id array (TAPED only)
   uint8_t* gb;       // this thread's slot in the flag array: bits 0-2 layer_num attr, bit 7 to_bottom
   int L;             // number of layers
   int n;             // total number of fronts
   unsigned cntpk;    // per-layer list lengths, 8 bits each
-  Soil soil[MAXL];
+  SoilT<R> soil[MAXL];
   double cum[MAXL];  // cumulative layer thickness (GlobalParams.py:103-110)
   double thick[MAXL];
   double pdm;        // ponded_depth_max
-  double psi_wp;     // AET: capillary head at which AET = 0.5 PET (aet.py:37-43); column constant
-  double ponded_water, previous_precip, ending_volume;
-  double giuh[NGIUH];
+  R psi_wp;          // AET: capillary head at which AET = 0.5 PET (aet.py:37-43); column constant
+  R ponded_water, ending_volume;
+  double previous_precip;
+  R giuh[NGIUH];
   bool empty_list;   // set by mass_balance() when a layer list is empty (IndexError in the reference)
 
   __device__ __forceinline__ double& f(int fld, int i) { return fb[(fld * FM + i) * NT]; }
+  __device__ __forceinline__ int& fid(int fld, int i) { return ib[(fld * FM + i) * NT]; }
+  // generic get / set of a field as R
+  __device__ __forceinline__ R g(int fld, int i) {
+    if constexpr (TAPED) return Var(f(fld, i), fid(fld, i));
+    else return f(fld, i);
+  }
+  __device__ __forceinline__ void s(int fld, int i, const R& x) {
+    if constexpr (TAPED) {
+      f(fld, i) = x.v;
+      fid(fld, i) = x.id;
+    } else {
+      f(fld, i) = x;
+    }
+  }
+  template <class Q>
+  __device__ __forceinline__ Q gq(int fld, int i) {
+    if constexpr (std::is_same<Q, double>::value) return f(fld, i);
+    else return g(fld, i);
+  }
   __device__ __forceinline__ int lay(int i) const { return gb[i * NT] & 7; }
   __device__ __forceinline__ bool tb(int i) const { return (gb[i * NT] & 0x80) != 0; }
   __device__ __forceinline__ void set_flag(int i, int layer, bool to_bottom) {
@@ -420,17 +664,12 @@ struct Column {
     for (int k = 0; k < l; k++) o += cnt(k);
     return o;
   }
-  __device__ __forceinline__ int list_layer(int i) const {  // which per-layer list holds flat index i
-    int o = 0;
-    for (int l = 0; l < L - 1; l++) {
-      o += cnt(l);
-      if (i < o) return l;
-    }
-    return L - 1;
-  }
   __device__ __forceinline__ void copy_front(int dst, int src) {
 #pragma unroll
-    for (int k = 0; k < 5; k++) f(k, dst) = f(k, src);
+    for (int k = 0; k < 5; k++) {
+      f(k, dst) = f(k, src);
+      if constexpr (TAPED) fid(k, dst) = fid(k, src);
+    }
     gb[dst * NT] = gb[src * NT];
   }
   // list.insert(0, front) on layer list l
@@ -457,26 +696,29 @@ struct Column {
   // Layer.get_len_layers (Layer.py:1145-1155)
   __device__ __forceinline__ int len_layers(int l) const { return (l < L - 1) ? cnt(l) : cnt(l) - 1; }
 
-  // ---- Layer.mass_balance (Layer.py:795-824); association S0 + (S1 + (S2 ...))
-  __device__ double mass_balance() {
-    double s_l[MAXL];
+  // ---- Layer.mass_balance (Layer.py:795-824); association S0 + (S1 + (S2 ...)).
+  //      Q = double evaluates values only (root-finder loops), Q = R is on the tape.
+  template <class Q>
+  __device__ Q mass_balance_t() {
+    Q s_l[MAXL];
     empty_list = false;
     int o = 0;
     for (int l = 0; l < L; l++) {
       const double base = (l == 0) ? 0.0 : (cum[l] - thick[l]);
       const int nf = cnt(l);
-      double sum = 0.0;
+      Q sum(0.0);
       for (int i = 0; i < nf - 1; i++)
-        sum = sum + (f(F_DEPTH, o + i) - base) * (f(F_THETA, o + i) - f(F_THETA, o + i + 1));
-      if (nf > 0) sum = sum + (f(F_DEPTH, o + nf - 1) - base) * f(F_THETA, o + nf - 1);
+        sum = sum + (gq<Q>(F_DEPTH, o + i) - base) * (gq<Q>(F_THETA, o + i) - gq<Q>(F_THETA, o + i + 1));
+      if (nf > 0) sum = sum + (gq<Q>(F_DEPTH, o + nf - 1) - base) * gq<Q>(F_THETA, o + nf - 1);
       else empty_list = true;  // wetting_fronts[0] of an empty list: IndexError in the reference
       s_l[l] = sum;
       o += nf;
     }
-    double tot = s_l[L - 1];
+    Q tot = s_l[L - 1];
     for (int l = L - 2; l >= 0; l--) tot = s_l[l] + tot;
     return tot;
   }
+  __device__ __forceinline__ R mass_balance() { return mass_balance_t<R>(); }
 
   // ---- free-drainage front (models/dpLGAR.py:328-338, Layer.py:134-162): arg-min psi, ties ->
   //      deeper; else-branch torch.isclose(psi_i, psi, atol=1e-8) with default rtol 1e-5
@@ -505,12 +747,13 @@ struct Column {
   //      depth is stepped by +/-0.01*factor (factor *= 0.001 at every down-switch) until the column
   //      mass error lies in [0, 2e-12].  The column mass is monotone in that depth, so long runs of
   //      equal steps are crossed with doubling/halving probes on depths computed by
-  //      advance_rounded(): the visited depths are exactly the reference's.
+  //      advance_rounded(): the visited depths are exactly the reference's.  Autograd: the depth is
+  //      shifted by constants only, so the tape id of the depth is kept (straight-through, Q14).
   __device__ void check_column_mass(int fd, double old_mass, double percolation, double aet, Ctx& c) {
     const double theta_e_k1 = soil[lay(fd)].the;
     const double mass_timestep = (old_mass + percolation) - (aet + 0.0);
     if (fabs(f(F_THETA, fd) - theta_e_k1) < 1e-12) {
-      double current_mass = mass_balance();
+      double current_mass = mass_balance_t<double>();
       double err = fabs(current_mass - mass_timestep);
       bool switched = false;
       double factor = 1.0;
@@ -537,7 +780,7 @@ struct Column {
           depth_new = depth_new - (0.01 * factor);
         }
         f(F_DEPTH, fd) = depth_new;
-        current_mass = mass_balance();
+        current_mass = mass_balance_t<double>();
         err = fabs(current_mass - mass_timestep);
         if (up == run_up && factor == fac_before) run_len++;
         else {
@@ -554,7 +797,7 @@ struct Column {
             c.cnt[C_COLMASS]++;
             const double cand = advance_rounded(depth_new, up ? step : -step, stride);
             f(F_DEPTH, fd) = cand;
-            const double m = mass_balance();
+            const double m = mass_balance_t<double>();
             const double e = fabs(m - mass_timestep);
             const bool cont = (up ? (m < mass_timestep) : !(m < mass_timestep)) && (fabs(e - 1e-12) > 1e-12) &&
                               (fabs(cand) >= 64.0 * step) && ((cand < 0.0) == (depth_new < 0.0)) &&
@@ -591,9 +834,11 @@ struct Column {
   //      fronts between copy_states() and here), and only the OLD theta/psi of the front below
   //      (previous_next_front) and the front's own old values are read, so the snapshot is carried in
   //      registers instead of a copy of the list.
+  //      Autograd (Q14): P1 and P2 only steer the search for psi, which is shifted by constants, so they
+  //      run on plain values; the tape sees theta = theta_l(scale * psi_in + const).
   enum Kind { K_NONE = 0, K_DEEPEST = 1, K_INLAYER0 = 2, K_INLAYER_DEEP = 3, K_BASE = 4 };
 
-  __device__ void move_wetting_fronts_warp(bool go, int fd, double infiltration, double aet, double old_mass,
+  __device__ void move_wetting_fronts_warp(bool go, int fd, const R& infiltration, const R& aet, const R& old_mass,
                                            double dt, Ctx& c) {
     const unsigned FULL = 0xffffffffu;
     go = go && (c.st == 0);
@@ -601,7 +846,7 @@ struct Column {
     int rmax = num_wf;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) rmax = max(rmax, __shfl_xor_sync(FULL, rmax, d));
-    double old_theta_below = 0.0, old_psi_below = 0.0;  // previous_state of front i+1
+    R old_theta_below(0.0), old_psi_below(0.0);  // previous_state of front i+1
     int l = L - 1;
     int o = go ? n - cnt(L - 1) : 0;  // flat offset of list l
     for (int r = 0; r < rmax; r++) {
@@ -611,7 +856,7 @@ struct Column {
       bool add_flux = false;
       double psi_cm = 0.0, psi_old = 0.0, psi_below = 0.0, psi_below_old = 0.0;
       double prior_mass = 0.0, new_mass = 0.0, own_dth = 0.0, own_dtk = 0.0;
-      double old_depth = 0.0, old_theta = 0.0, old_psi = 0.0;
+      R old_depth(0.0), old_theta(0.0), old_psi(0.0), psi_in(0.0);
       if (mine) {
         while (i < o) {  // step to the list above
           l--;
@@ -619,44 +864,46 @@ struct Column {
         }
         lyr = l;
         const int last = o + cnt(l) - 1;  // wetting_fronts[-1] of this list
-        old_depth = f(F_DEPTH, i);
-        old_theta = f(F_THETA, i);
-        old_psi = f(F_PSI, i);
+        old_depth = g(F_DEPTH, i);
+        old_theta = g(F_THETA, i);
+        old_psi = g(F_PSI, i);
         if (i < num_wf - 1) {
           if (is_equal(i, last)) {
             // deepest_layer_front (Layer.py:389-418): theta = theta_l(psi of the front below)
             if (!(i < last || l < L - 1)) raise(c, LGAR_ST_NULL_NEIGHBOUR);
             kind = K_DEEPEST;
-            psi_cm = f(F_PSI, i + 1);
+            psi_in = g(F_PSI, i + 1);
+            psi_cm = val(psi_in);
           } else {
             // wetting_front_in_layer (Layer.py:420-547); i < last, so next is in the same list
-            const double dzdt = f(F_DZDT, i);
+            const R dzdt = g(F_DZDT, i);
             if (l == 0) {
               kind = K_INLAYER0;
-              double pm = old_depth * (old_theta - old_theta_below);
+              R pm = old_depth * (old_theta - old_theta_below);
               if (is_equal(fd, i)) pm = pm + (infiltration - (0.0 + aet));
-              double depth = old_depth + (dzdt * dt);
+              R depth = old_depth + (dzdt * dt);
               depth = tmin(depth, cum[L - 1]);
-              f(F_DEPTH, i) = depth;
-              const bool zero_dzdt = fabs(dzdt) <= 1e-8;  // isclose(dzdt, 0, rtol=1e-8) (Q2)
+              s(F_DEPTH, i, depth);
+              const bool zero_dzdt = vabs(dzdt) <= 1e-8;  // isclose(dzdt, 0, rtol=1e-8) (Q2)
               if (!(zero_dzdt && !tb(i))) {
-                double potential_theta = (pm / depth) + f(F_THETA, i + 1);
-                f(F_THETA, i) = tmin(soil[0].the, potential_theta);
+                R potential_theta = (pm / depth) + g(F_THETA, i + 1);
+                s(F_THETA, i, tmin(soil[0].the, potential_theta));
               }
             } else {
               kind = K_INLAYER_DEEP;
               const double plt = cum[l - 1];
-              const double depth = old_depth + (dzdt * dt);
-              f(F_DEPTH, i) = depth;
-              psi_old = old_psi;
-              psi_below_old = old_psi_below;
-              psi_cm = old_psi;
+              const R depth = old_depth + (dzdt * dt);
+              s(F_DEPTH, i, depth);
+              psi_in = old_psi;
+              psi_old = val(old_psi);
+              psi_below_old = val(old_psi_below);
+              psi_cm = val(old_psi);
               psi_below = f(F_PSI, i + 1);
-              prior_mass = (old_depth - plt) * (old_theta - old_theta_below);
-              new_mass = (depth - plt) * (old_theta - f(F_THETA, i + 1));
+              prior_mass = (val(old_depth) - plt) * (val(old_theta) - val(old_theta_below));
+              new_mass = (val(depth) - plt) * (val(old_theta) - f(F_THETA, i + 1));
               nup = l;
               own_dth = f(F_THETA, i + 1);
-              own_dtk = depth - plt;
+              own_dtk = val(depth) - plt;
               add_flux = is_equal(fd, i);
             }
           }
@@ -664,21 +911,22 @@ struct Column {
         if (num_wf == L && l == L - 1) {
           // base_case (Layer.py:320-387): one front per layer, this is the bottom one
           kind = K_BASE;
-          const double depth = f(F_DEPTH, i) + f(F_DZDT, i) * dt;
-          f(F_DEPTH, i) = depth;
-          psi_old = old_psi;
-          psi_cm = f(F_PSI, i);
+          const R depth = g(F_DEPTH, i) + g(F_DZDT, i) * dt;
+          s(F_DEPTH, i, depth);
+          psi_in = g(F_PSI, i);
+          psi_old = val(old_psi);
+          psi_cm = val(psi_in);
           const double base = (l > 0) ? cum[l - 1] : 0.0;
-          prior_mass = (old_depth - base) * (old_theta - 0.0);
-          new_mass = (depth - base) * (f(F_THETA, i) - 0.0);
+          prior_mass = (val(old_depth) - base) * (val(old_theta) - 0.0);
+          new_mass = (val(depth) - base) * (f(F_THETA, i) - 0.0);
           if (L < 2) raise(c, LGAR_ST_NULL_NEIGHBOUR);
           nup = L - 1;
           own_dth = 0.0;
-          own_dtk = depth - base;
+          own_dtk = val(depth) - base;
           add_flux = (lay(fd) == l);
         }
       }
-      // ---- P1: sums over the layers above (convergent)
+      // ---- P1: sums over the layers above (convergent, values only)
       double dth[MAXL - 1], dtk[MAXL - 1];
       int nupmax = nup;
 #pragma unroll
@@ -709,23 +957,26 @@ struct Column {
           }
         }
       }
-      if (add_flux) prior_mass = prior_mass + infiltration - (0.0 + aet);
+      if (add_flux) prior_mass = prior_mass + val(infiltration) - (0.0 + val(aet));
 
-      // ---- P2: batched theta_mass_balance
+      // ---- P2: batched theta_mass_balance (values only)
       const double tol = 1e-12;
       const Soil own = soil[lyr];  // hoisted into registers for the iteration loop
       const Soil up0 = soil[0];
       const Soil up1 = soil[(MAXL > 2) ? 1 : 0];
       double delta_mass = fabs(new_mass - prior_mass);
       double theta = 0.0;
+      double psi_scale = 1.0;   // d psi_final / d psi_in: 0.1 per `psi = psi_prev * 0.1` guard hit
+      bool have_theta = false;  // theta already holds theta_l(psi_cm) (value)
       const bool wants = mine && (kind == K_DEEPEST || kind >= K_INLAYER_DEEP) && (c.st == 0);
       // early return `delta_mass <= tolerance` (and the deepest-front case): one evaluation
-      if (wants && (kind == K_DEEPEST || delta_mass <= tol)) theta = theta_from_h(psi_cm, own, c);
+      const bool single = wants && (kind == K_DEEPEST || delta_mass <= tol);
       bool active = wants && kind >= K_INLAYER_DEEP && (delta_mass > tol);
       {
         bool switched = false;
         double factor = 1.0;
         double psi_prev = psi_cm;
+        double prev_scale = 1.0;
         double delta_mass_prev = delta_mass;
         int count_no_mass_change = 0;
         long long it = 0;
@@ -751,12 +1002,14 @@ struct Column {
             const bool up = probe ? run_up : (new_mass > prior_mass);
             double step;
             double psi_try, psi_prev_try = psi_prev;
+            double scale_try = psi_scale, prev_scale_try = prev_scale;
             bool sw = switched;
             double fac = factor;
             if (probe) {
               step = 0.1 * factor;
               psi_try = advance_rounded(psi_cm, up ? step : -step, stride);
               if (!up) psi_prev_try = advance_rounded(psi_cm, -step, stride - 1);
+              if (!up) prev_scale_try = psi_scale;
             } else if (up) {
               step = 0.1 * factor;
               psi_try = psi_cm + step;
@@ -768,8 +1021,12 @@ struct Column {
               }
               step = 0.1 * fac;
               psi_prev_try = psi_cm;
+              prev_scale_try = psi_scale;
               psi_try = psi_cm - step;
-              if (psi_try < 0.0 && psi_prev_try != 0.0) psi_try = psi_prev_try * 0.1;
+              if (psi_try < 0.0 && psi_prev_try != 0.0) {
+                psi_try = psi_prev_try * 0.1;
+                scale_try = prev_scale_try * 0.1;
+              }
             }
             Ctx cc;  // guards raised by a rejected probe must not kill the column
             cc.st = 0;
@@ -799,7 +1056,9 @@ struct Column {
               if (ok) {  // identical to `stride` regular iterations of this run
                 psi_cm = psi_try;
                 psi_prev = psi_prev_try;
+                prev_scale = prev_scale_try;
                 theta = th;
+                have_theta = true;
                 new_mass = mass_layers;
                 delta_mass = dm;
                 delta_mass_prev = dm;
@@ -822,9 +1081,12 @@ struct Column {
               }
               psi_cm = psi_try;
               psi_prev = psi_prev_try;
+              psi_scale = scale_try;
+              prev_scale = prev_scale_try;
               switched = sw;
               factor = fac;
               theta = th;
+              have_theta = true;
               new_mass = mass_layers;
               delta_mass = dm;
               bool stop = !(delta_mass > tol);
@@ -847,21 +1109,28 @@ struct Column {
           }
         }
       }
-      // ---- P3: store theta, psi = h(Se(theta)) tail
-      if (mine && c.st == 0) {
+      // ---- P3: theta = theta_l(psi_final) on the tape, psi = h(Se(theta)) tail
+      if (mine && c.st == 0 && (kind == K_DEEPEST || kind >= K_INLAYER_DEEP)) {
+        R thR(0.0);  // NaN delta_mass: the reference returns its initial theta = 0.0
+        if (single) {
+          thR = thetaR(psi_in, soil[lyr], c);
+        } else if (have_theta) {
+          if constexpr (TAPED) thR = thetaR(scaled_shift(psi_in, psi_cm, psi_scale), soil[lyr], c);
+          else thR = theta;  // the loop's last evaluation is theta_l(psi_final)
+        }
         if (kind == K_DEEPEST) {
-          f(F_THETA, i) = theta;
-          f(F_PSI, i) = psi_cm;
-        } else if (kind >= K_INLAYER_DEEP) {
-          f(F_THETA, i) = tmin(theta, own.the);
+          s(F_THETA, i, thR);
+          s(F_PSI, i, psi_in);
+        } else {
+          s(F_THETA, i, tmin(thR, soil[lyr].the));
         }
       }
       if (mine && kind >= K_INLAYER0 && c.st == 0) {
-        double se = se_from_theta(f(F_THETA, i), own, c);
-        f(F_PSI, i) = h_from_se(se, own, c);
+        R se = se_thetaR(g(F_THETA, i), soil[lyr], c);
+        s(F_PSI, i, h_seR(se, soil[lyr], c));
       }
       if (mine) {
-        if (i == 0 && c.st == 0) check_column_mass(fd, old_mass, infiltration, aet, c);
+        if (i == 0 && c.st == 0) check_column_mass(fd, val(old_mass), val(infiltration), val(aet), c);
         old_theta_below = old_theta;
         old_psi_below = old_psi;
       }
@@ -902,13 +1171,13 @@ struct Column {
             raise(c, LGAR_ST_NULL_NEIGHBOUR);  // Q10
             break;
           }
-          const Soil& s = soil[l];
-          const double th_c = f(F_THETA, i), th_n = f(F_THETA, nx), th_2 = f(F_THETA, n2);
-          double mass = f(F_DEPTH, i) * (th_c - th_n) + f(F_DEPTH, nx) * (th_n - th_2);
-          f(F_DEPTH, i) = mass / (th_c - th_2);
-          double se = se_from_theta(th_c, s, c);
-          f(F_PSI, i) = h_from_se(se, s, c);
-          f(F_K, i) = k_from_se(se, s.ksat, s.m, s.inv_m, c);
+          const SoilT<R>& sl = soil[l];
+          const R th_c = g(F_THETA, i), th_n = g(F_THETA, nx), th_2 = g(F_THETA, n2);
+          R mass = g(F_DEPTH, i) * (th_c - th_n) + g(F_DEPTH, nx) * (th_n - th_2);
+          s(F_DEPTH, i, mass / (th_c - th_2));
+          R se = se_thetaR(th_c, sl, c);
+          s(F_PSI, i, h_seR(se, sl, c));
+          s(F_K, i, k_seR(se, sl, c));
           // delete_front (:888-892): pop the first front of THIS list that is value-equal to next
           const int nf = cnt(l);
           for (int q = 0; q < nf; q++) {
@@ -929,36 +1198,36 @@ struct Column {
     int o = 0;
     for (int l = 0; l < L; l++) {
       const int lf = len_layers(l);
-      const Soil& s = soil[l];
+      const SoilT<R>& sl = soil[l];
       for (int j = 0; j < lf; j++) {
         const int i = o + j, nx = i + 1;
         const bool deeper = f(F_DEPTH, i) > cum[l];
         const bool next_at_boundary = f(F_DEPTH, nx) == cum[l];
         if (deeper && next_at_boundary) {
-          const double overshot = f(F_DEPTH, i) - f(F_DEPTH, nx);
-          double se = se_from_theta(f(F_THETA, i), s, c);
-          const double psi_c = h_from_se(se, s, c);
-          f(F_PSI, i) = psi_c;
-          f(F_K, i) = k_from_se(se, s.ksat, s.m, s.inv_m, c);
+          const R overshot = g(F_DEPTH, i) - g(F_DEPTH, nx);
+          R se = se_thetaR(g(F_THETA, i), sl, c);
+          const R psi_c = h_seR(se, sl, c);
+          s(F_PSI, i, psi_c);
+          s(F_K, i, k_seR(se, sl, c));
           if (l >= L - 1) {  // recalibrate dereferences self.next_layer (None): Q9
             raise(c, LGAR_ST_BOTTOM_REACHED);
             return;
           }
           const int n2 = next_to_next(l, o, j);
-          double theta_new = theta_from_h(psi_c, soil[l + 1], c);
-          double mbal = overshot * (f(F_THETA, i) - f(F_THETA, nx));
+          R theta_new = thetaR(psi_c, soil[l + 1], c);
+          R mbal = overshot * (g(F_THETA, i) - g(F_THETA, nx));
           if (n2 < 0) {
             raise(c, LGAR_ST_NULL_NEIGHBOUR);
             return;
           }
-          double mbal_z = mbal / (theta_new - f(F_THETA, n2));
-          double depth_new = cum[l] + mbal_z;
-          f(F_DEPTH, i) = cum[l];
-          f(F_THETA, nx) = theta_new;
-          f(F_PSI, nx) = psi_c;
-          f(F_DEPTH, nx) = depth_new;
-          f(F_DZDT, nx) = f(F_DZDT, i);
-          f(F_DZDT, i) = 0.0;
+          R mbal_z = mbal / (theta_new - g(F_THETA, n2));
+          R depth_new = cum[l] + mbal_z;
+          s(F_DEPTH, i, R(cum[l]));
+          s(F_THETA, nx, theta_new);
+          s(F_PSI, nx, psi_c);
+          s(F_DEPTH, nx, depth_new);
+          s(F_DZDT, nx, g(F_DZDT, i));
+          s(F_DZDT, i, R(0.0));
           set_flag(nx, l + 1, false);
           set_flag(i, lay(i), true);
         }
@@ -982,13 +1251,13 @@ struct Column {
             // pop(j) from list l and insert at the head of list l+1: rotate [o+j, o+nf)
             const int from = o + j, to = o + nf - 1;
             if (from != to) {
-              double t5[5];
+              R t5[5];
 #pragma unroll
-              for (int k = 0; k < 5; k++) t5[k] = f(k, from);
+              for (int k = 0; k < 5; k++) t5[k] = g(k, from);
               uint8_t tg = gb[from * NT];
               for (int q = from; q < to; q++) copy_front(q, q + 1);
 #pragma unroll
-              for (int k = 0; k < 5; k++) f(k, to) = t5[k];
+              for (int k = 0; k < 5; k++) s(k, to, t5[k]);
               gb[to * NT] = tg;
             }
             add_cnt(l, -1);
@@ -1008,54 +1277,54 @@ struct Column {
   //      parameters, sic) and it is popped.  Reachable for the last front of layer L-2 when the
   //      last layer holds a single front.  The loop bound is evaluated before the pops, like
   //      Python's range(): an index past the shortened list raises IndexError.
-  __device__ double cross_domain_boundary(Ctx& c) {
-    double fl[MAXL];
+  __device__ R cross_domain_boundary(Ctx& c) {
+    R fl[MAXL];
     int o = 0;
     for (int l = 0; l < L; l++) {
-      fl[l] = 0.0;
+      fl[l] = R(0.0);
       const int lf = len_layers(l);
-      const Soil& s = soil[l];
+      const SoilT<R>& sl = soil[l];
       for (int j = 0; j < lf; j++) {
         if (j >= cnt(l)) {
           raise(c, LGAR_ST_INDEX_ERROR);
-          return 0.0;
+          return R(0.0);
         }
         const int n2 = next_to_next(l, o, j);
         if (n2 == -2) {
           raise(c, LGAR_ST_NULL_NEIGHBOUR);
-          return 0.0;
+          return R(0.0);
         }
-        double tmp = 0.0;
+        R tmp(0.0);
         const int i = o + j;
         if (n2 == -1 && f(F_DEPTH, i) > cum[l]) {
           const bool has_next = (j < cnt(l) - 1) || (l < L - 1);
           if (!has_next) {
             raise(c, LGAR_ST_NULL_NEIGHBOUR);
-            return 0.0;
+            return R(0.0);
           }
           const int nx = i + 1;
-          tmp = (f(F_THETA, i) - f(F_THETA, nx)) * (f(F_DEPTH, i) - f(F_DEPTH, nx));
-          f(F_THETA, nx) = f(F_THETA, i);
-          double se_k = se_from_theta(f(F_THETA, i), s, c);
-          f(F_PSI, nx) = h_from_se(se_k, s, c);
-          f(F_K, nx) = k_from_se(se_k, s.ksat, s.m, s.inv_m, c);
+          tmp = (g(F_THETA, i) - g(F_THETA, nx)) * (g(F_DEPTH, i) - g(F_DEPTH, nx));
+          s(F_THETA, nx, g(F_THETA, i));
+          R se_k = se_thetaR(g(F_THETA, i), sl, c);
+          s(F_PSI, nx, h_seR(se_k, sl, c));
+          s(F_K, nx, k_seR(se_k, sl, c));
           erase_at(i, l);
         }
         fl[l] = fl[l] + tmp;
       }
       o += cnt(l);
     }
-    double tot = fl[L - 1];
+    R tot = fl[L - 1];
     for (int l = L - 2; l >= 0; l--) tot = fl[l] + tot;
     return tot;
   }
 
   // ---- Layer.fix_dry_over_wet_fronts (Layer.py:1055-1143): one fix per layer list per call
-  __device__ double fix_dry_over_wet(Ctx& c) {
-    double mc[MAXL];
+  __device__ R fix_dry_over_wet(Ctx& c) {
+    R mc[MAXL];
     int o = 0;
     for (int l = 0; l < L; l++) {
-      mc[l] = 0.0;
+      mc[l] = R(0.0);
       const int nf = cnt(l);
       for (int j = 0; j < nf; j++) {
         const int i = o + j;
@@ -1063,18 +1332,18 @@ struct Column {
         if (!has_next) continue;
         const int nx = i + 1;
         if (f(F_THETA, i) <= f(F_THETA, nx) && lay(i) == lay(nx)) {
-          const double mass_before = mass_balance();
+          const R mass_before = mass_balance();
           const int popped_layer = lay(i);
           erase_at(i, l);  // the former next front now sits at flat index i
           if (popped_layer > 0) cleanup_wetting_fronts(i, c);
-          const double mass_after = mass_balance();
-          mc[l] = mc[l] + fabs(mass_after - mass_before);
+          const R mass_after = mass_balance();
+          mc[l] = mc[l] + abs_(mass_after - mass_before);
           break;
         }
       }
       o += cnt(l);
     }
-    double tot = mc[L - 1];
+    R tot = mc[L - 1];
     for (int l = L - 2; l >= 0; l--) tot = mc[l] + tot;
     return tot;
   }
@@ -1086,20 +1355,20 @@ struct Column {
       for (int j = 0; j < nf; j++) {
         const int i = o + j;
         if (is_equal(i, nx)) {
-          const Soil& s = soil[l];
-          double se_k = se_from_theta(f(F_THETA, i), s, c);
-          f(F_PSI, i) = h_from_se(se_k, s, c);
+          const SoilT<R>& sl = soil[l];
+          R se_k = se_thetaR(g(F_THETA, i), sl, c);
+          s(F_PSI, i, h_seR(se_k, sl, c));
           // update_layer_fronts (:1117-1143, Q15): every front of every list above dry.layer_num
           const int dry_layer = lay(i);
-          const double dry_theta = f(F_THETA, i), dry_psi = f(F_PSI, i);
+          const R dry_theta = g(F_THETA, i), dry_psi = g(F_PSI, i);
           int o2 = 0;
           for (int l2 = 0; l2 < L && l2 < dry_layer; l2++) {
-            const Soil& s2 = soil[l2];
+            const SoilT<R>& s2 = soil[l2];
             const int nf2 = cnt(l2);
             for (int q = 0; q < nf2; q++) {
-              double se_l = se_from_theta(dry_theta, s2, c);
-              f(F_PSI, o2 + q) = h_from_se(se_l, s2, c);
-              f(F_THETA, o2 + q) = theta_from_h(dry_psi, s2, c);
+              R se_l = se_thetaR(dry_theta, s2, c);
+              s(F_PSI, o2 + q, h_seR(se_l, s2, c));
+              s(F_THETA, o2 + q, thetaR(dry_psi, s2, c));
             }
             o2 += nf2;
           }
@@ -1126,22 +1395,22 @@ struct Column {
           l++;
           o_next += cnt(l);
         }
-        const Soil& s = soil[l];
-        double se = se_from_theta(f(F_THETA, i), s, c);
-        const double2 pk = psi_k_from_se(se, s, c);
-        f(F_PSI, i) = pk.x;
-        f(F_K, i) = pk.y;
+        const SoilT<R>& sl = soil[l];
+        R se = se_thetaR(g(F_THETA, i), sl, c);
+        const Pair<R> pk = psi_kR(se, sl, c);
+        s(F_PSI, i, pk.x);
+        s(F_K, i, pk.y);
       }
     }
   }
 
   // ---- Layer.calc_bottom_sum (Layer.py:1557-1582) from list l0 upward in index
-  __device__ double calc_bottom_sum(int l0, double bottom_sum, double psi, int front_layer, Ctx& c) {
+  __device__ R calc_bottom_sum(int l0, R bottom_sum, const R& psi, int front_layer, Ctx& c) {
     for (int k = l0;; k++) {
-      const Soil& sk = soil[k];
-      double theta_prev = theta_from_h(psi, sk, c);
-      double se_prev = se_from_theta(theta_prev, sk, c);
-      double kk = k_from_se(se_prev, sk.ksat, sk.m, sk.inv_m, c);
+      const SoilT<R>& sk = soil[k];
+      R theta_prev = thetaR(psi, sk, c);
+      R se_prev = se_thetaR(theta_prev, sk, c);
+      R kk = k_seR(se_prev, sk, c);
       double plt = (k != 0) ? cum[k - 1] : 0.0;
       bottom_sum = bottom_sum + ((cum[k] - plt) / kk);
       if (k + 1 >= L) {
@@ -1154,10 +1423,10 @@ struct Column {
 
   // ---- dpLGAR.move_wetting_front (models/dpLGAR.py:340-367); returns the bottom flux.
   //      Warp-convergent (every lane calls; `go` selects the lanes that actually move fronts).
-  __device__ double move_wetting_front_warp(bool go, int fd, double infiltration, double& AET_sub, double old_mass,
-                                            double dt, Ctx& c) {
+  __device__ R move_wetting_front_warp(bool go, int fd, const R& infiltration, R& AET_sub, const R& old_mass, double dt,
+                                       Ctx& c) {
     move_wetting_fronts_warp(go, fd, infiltration, AET_sub, old_mass, dt, c);
-    double bottom_flux = 0.0;
+    R bottom_flux(0.0);
     if (go && c.st == 0) {
       merge_wetting_fronts(c);
       cross_layer_boundary(c);
@@ -1167,9 +1436,9 @@ struct Column {
       // (fix_dry_over_wet_fronts -> get_neighboring_fronts / mass_balance) raises IndexError
       for (int l = 0; l < L; l++)
         if (cnt(l) == 0) raise(c, LGAR_ST_INDEX_ERROR);
-      double mass_change = 0.0;
+      R mass_change(0.0);
       if (c.st == 0) mass_change = fix_dry_over_wet(c);
-      if (fabs(mass_change) > 1e-7) AET_sub = AET_sub - mass_change;
+      if (vabs(mass_change) > 1e-7) AET_sub = AET_sub - mass_change;
     }
     update_psi_warp(go, c);
     return bottom_flux;

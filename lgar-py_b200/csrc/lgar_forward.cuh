@@ -43,86 +43,87 @@ struct KParams {
   long long iter_cap;
 };
 
-template <int FM>
+template <int FM, class R>
 struct Tile {
-  Column<FM> col;
+  Column<FM, R> col;
   Ctx ctx;
-  double acc[NOUT];   // per-forcing-step accumulators (reset every step)
+  R acc[NOUT];        // per-forcing-step accumulators (reset every step)
   double sums[NOUT];  // running sums over time
   int crash_step;
   int psiwp_st;       // guard raised while precomputing psi_wp (reported on first AET use)
 };
 
 // ---- Layer.calc_aet (Layer.py:760-783) -> calc_aet (lgar/aet.py:17-51)
-template <int FM>
-__device__ __forceinline__ void precompute_psi_wp(Tile<FM>& T, double wilting_psi) {
+template <int FM, class R>
+__device__ __forceinline__ void precompute_psi_wp(Tile<FM, R>& T, double wilting_psi) {
   Ctx cc = T.ctx;
   cc.st = 0;
-  const Soil& s = T.col.soil[0];
+  const SoilT<R>& s = T.col.soil[0];
   double theta_fc = (s.the - s.thr) * 0.75 + s.thr;  // GlobalParams.py:75
-  double wp_head_theta = theta_from_h(wilting_psi, s, cc);
-  double theta_wp = (theta_fc - wp_head_theta) * 0.5 + wp_head_theta;
-  double se = se_from_theta(theta_wp, s, cc);
-  T.col.psi_wp = h_from_se(se, s, cc);
+  R wp_head_theta = thetaR(R(wilting_psi), s, cc);
+  R theta_wp = (theta_fc - wp_head_theta) * 0.5 + wp_head_theta;
+  R se = se_thetaR(theta_wp, s, cc);
+  T.col.psi_wp = h_seR(se, s, cc);
   T.psiwp_st = cc.st;
 }
-template <int FM>
-__device__ __forceinline__ double calc_aet(Tile<FM>& T, double pet, double dt) {
+__device__ __forceinline__ double pow3R(double x, Ctx& c) { return safe_pow(x, 3.0, c); }
+__device__ __forceinline__ Var pow3R(const Var& x, Ctx& c) { return pow3_(x, safe_pow(x.v, 3.0, c)); }
+template <int FM, class R>
+__device__ __forceinline__ R calc_aet(Tile<FM, R>& T, double pet, double dt) {
   Ctx& c = T.ctx;
   if (T.psiwp_st) raise(c, T.psiwp_st);
   c.cnt[C_THETA_H] += 1;
   c.cnt[C_H_SE] += 1;
-  double h_ratio = 1.0 + safe_pow(T.col.f(F_PSI, 0) / T.col.psi_wp, 3.0, c);
-  double aet_ = pet * (1.0 / h_ratio) * dt;
-  double r = (aet_ < 0.0) ? 0.0 : aet_;  // torch.clamp(min=0, max=pet): upper clamp is the RATE (sic)
-  r = (r > pet) ? pet : r;
-  return r;
+  R h_ratio = 1.0 + pow3R(T.col.g(F_PSI, 0) / T.col.psi_wp, c);
+  R aet_ = pet * (1.0 / h_ratio) * dt;
+  return clamp_(aet_, 0.0, pet);  // torch.clamp(min=0, max=pet): upper clamp is the RATE (sic)
 }
 
 // set_internal_states (models/dpLGAR.py:97-147), Layer.__init__ (Layer.py:22-90),
 // WettingFront.__init__ (WettingFront.py:18-49), generate_soil_metrics (data/utils.py:40-105)
-template <int FM>
-__device__ void init_column(Tile<FM>& T, double initial_psi) {
-  Column<FM>& C = T.col;
+template <int FM, class R>
+__device__ void init_column(Tile<FM, R>& T, double initial_psi) {
+  Column<FM, R>& C = T.col;
   Ctx& c = T.ctx;
   C.n = 0;
   C.cntpk = 0;
   for (int l = 0; l < C.L; l++) {
-    const Soil& s = C.soil[l];
-    double theta_init = theta_from_h(initial_psi, s, c);
+    const SoilT<R>& s = C.soil[l];
+    R theta_init = thetaR(R(initial_psi), s, c);
     const int i = C.n;
-    C.f(F_DEPTH, i) = C.cum[l];
-    C.f(F_THETA, i) = theta_init;
-    C.f(F_DZDT, i) = 0.0;
-    double se = se_from_theta(theta_init, s, c);
-    C.f(F_PSI, i) = initial_psi;
-    C.f(F_K, i) = k_from_se(se, s.ksat, s.m, s.inv_m, c);
+    C.s(F_DEPTH, i, R(C.cum[l]));
+    C.s(F_THETA, i, theta_init);
+    C.s(F_DZDT, i, R(0.0));
+    R se = se_thetaR(theta_init, s, c);
+    C.s(F_PSI, i, R(initial_psi));
+    C.s(F_K, i, k_seR(se, s, c));
     C.set_flag(i, l, true);
     C.n++;
     C.add_cnt(l, 1);
   }
   C.ending_volume = C.mass_balance();
-  C.ponded_water = 0.0;
+  C.ponded_water = R(0.0);
   C.previous_precip = 0.0;
-  for (int i = 0; i < NGIUH; i++) C.giuh[i] = 0.0;
+  for (int i = 0; i < NGIUH; i++) C.giuh[i] = R(0.0);
   for (int k = 0; k < NOUT; k++) T.sums[k] = 0.0;
 }
 
 // ---- one sub-step: models/dpLGAR.py:176-298.  Warp-convergent: every lane of the warp calls it;
 //      lanes with act == false only take part in the cooperative Geff evaluations.
-template <int FM>
-__device__ void substep(Tile<FM>& T, bool act, double precip_rate, double pet_rate, const KParams& K,
+template <int FM, class R>
+__device__ void substep(Tile<FM, R>& T, bool act, double precip_rate, double pet_rate, const KParams& K,
                         double* nodebuf) {
-  Column<FM>& C = T.col;
+  Column<FM, R>& C = T.col;
   Ctx& c = T.ctx;
   const double dt = K.p.subcycle_length_h;
   const int nint = K.p.nint;
   const int L = C.L;
   act = act && (c.st == 0);
 
-  double precip_sub = 0.0, ponded_depth_sub = 0.0, ponded_water_sub = 0.0, percolation_sub = 0.0;
-  double runoff_sub = 0.0, infiltration_sub = 0.0, AET_sub = 0.0;
-  double ending_volume_sub = C.ending_volume;
+  double precip_sub = 0.0;
+  R ponded_depth_sub(0.0), ponded_water_sub(0.0), percolation_sub(0.0);
+  R runoff_sub(0.0), infiltration_sub(0.0), AET_sub(0.0);
+  R ending_volume_sub = C.ending_volume;
   bool create = false, saturated = false;
   int fd = 0;
   if (act) {
@@ -144,7 +145,7 @@ __device__ void substep(Tile<FM>& T, bool act, double precip_rate, double pet_ra
   {
     int lfp = 0, nx_fd = 0;
     bool needG = false;
-    double theta_1 = 0.0, theta_2 = 0.0;
+    R theta_1(0.0), theta_2(0.0);
     if (brB) {
       lfp = C.lay(fd);
       const int o = C.off(lfp);
@@ -153,48 +154,45 @@ __device__ void substep(Tile<FM>& T, bool act, double precip_rate, double pet_ra
       else raise(c, LGAR_ST_NULL_NEIGHBOUR);
       if (c.st == 0 && C.n != L) {
         needG = true;
-        theta_1 = C.f(F_THETA, nx_fd);
-        theta_2 = C.soil[lfp].the;
+        theta_1 = C.g(F_THETA, nx_fd);
+        theta_2 = R(C.soil[lfp].the);
       }
     }
-    const double geff = geff_warp(needG, theta_1, theta_2, C.soil[needG ? lfp : 0], nint, nodebuf, c);
+    const R geff = geff_warpR(needG, theta_1, theta_2, C.soil[needG ? lfp : 0], nint, nodebuf, c);
     if (brB && c.st == 0) {
-      const double h_p_ = (ponded_depth_sub - precip_sub) * dt;
-      const double h_p = (h_p_ < 0.0) ? 0.0 : h_p_;  // clamp(min=0)
-      const double fd_depth = C.f(F_DEPTH, fd);
-      double f_p = 0.0;
+      const R h_p = clamp_min_((ponded_depth_sub - precip_sub) * dt, 0.0);  // clamp(min=0)
+      const R fd_depth = C.g(F_DEPTH, fd);
+      R f_p(0.0);
       if (lfp == 0) {
-        f_p = C.soil[0].ksat * (1.0 + (geff + h_p) / fd_depth);
+        f_p = C.soil[0].ksatR() * (1.0 + (geff + h_p) / fd_depth);
       } else if (C.n == L) {
         raise(c, LGAR_ST_NULL_NEIGHBOUR);  // `free_drainage_ksat` unbound in the reference
       } else {
-        const double fd_ksat = C.soil[lfp].ksat * K.p.frozen_factor;
-        double bottom_sum = (fd_depth - C.cum[lfp - 1]) / fd_ksat;
+        const R fd_ksat = C.soil[lfp].ksatR() * K.p.frozen_factor;
+        R bottom_sum = (fd_depth - C.cum[lfp - 1]) / fd_ksat;
         // calc_bottom_sum_f_p (:1538-1555, Q18): saturated K for layer 0, then the
         // unsaturated calc_bottom_sum for the remaining upper layers
-        const double k0 = C.soil[0].ksat * K.p.frozen_factor;
+        const R k0 = C.soil[0].ksatR() * K.p.frozen_factor;
         bottom_sum = bottom_sum + ((C.cum[0] - 0.0) / k0);
-        if (1 != lfp) bottom_sum = C.calc_bottom_sum(1, bottom_sum, C.f(F_PSI, fd), lfp, c);
+        if (1 != lfp) bottom_sum = C.calc_bottom_sum(1, bottom_sum, C.g(F_PSI, fd), lfp, c);
         f_p = (fd_depth / bottom_sum) + ((geff + h_p) * fd_ksat / fd_depth);
       }
-      const double pt_ = ponded_depth_sub - f_p * dt - 0.0;
-      const double ponded_temp = (pt_ < 0.0) ? 0.0 : pt_;
-      const double fp_cm = f_p * dt + 0.0 / dt;
+      const R ponded_temp = clamp_min_(ponded_depth_sub - f_p * dt - 0.0, 0.0);
+      const R fp_cm = f_p * dt + 0.0 / dt;
       if (C.pdm > 0.0) {
         if (ponded_temp < C.pdm) {
           infiltration_sub = tmin(ponded_depth_sub, fp_cm);
           ponded_depth_sub = ponded_depth_sub - infiltration_sub;
         } else if (ponded_temp > C.pdm) {
-          ponded_depth_sub = C.pdm;
+          ponded_depth_sub = R(C.pdm);
           infiltration_sub = fp_cm;
         }
-        const double r_ = ponded_temp - C.pdm;
-        runoff_sub = (r_ < 0.0) ? 0.0 : r_;
+        runoff_sub = clamp_min_(ponded_temp - C.pdm, 0.0);
       } else {
         infiltration_sub = tmin(ponded_depth_sub, fp_cm);
-        const double r_ = ponded_depth_sub - infiltration_sub;
-        ponded_depth_sub = C.pdm;
-        runoff_sub = (r_ < 0.0) ? 0.0 : r_;
+        const R r_ = ponded_depth_sub - infiltration_sub;
+        ponded_depth_sub = R(C.pdm);
+        runoff_sub = clamp_min_(r_, 0.0);
       }
       T.acc[LGAR_OUT_INFILTRATION] = T.acc[LGAR_OUT_INFILTRATION] + infiltration_sub;
       T.acc[LGAR_OUT_RUNOFF] = T.acc[LGAR_OUT_RUNOFF] + runoff_sub;
@@ -207,8 +205,8 @@ __device__ void substep(Tile<FM>& T, bool act, double precip_rate, double pet_ra
   //      with its infiltration).  models/dpLGAR.py:206-212 and :249-266
   {
     const bool go = act && c.st == 0 && (brA || !create);
-    const double infil_arg = create ? 0.0 : infiltration_sub;
-    const double bottom = C.move_wetting_front_warp(go, fd, infil_arg, AET_sub, ending_volume_sub, dt, c);
+    const R infil_arg = create ? R(0.0) : infiltration_sub;
+    const R bottom = C.move_wetting_front_warp(go, fd, infil_arg, AET_sub, ending_volume_sub, dt, c);
     if (go && !create) {
       percolation_sub = bottom;
       T.acc[LGAR_OUT_PERCOLATION] = T.acc[LGAR_OUT_PERCOLATION] + percolation_sub;
@@ -218,40 +216,40 @@ __device__ void substep(Tile<FM>& T, bool act, double precip_rate, double pet_ra
   // ---- phase 3: calc_dry_depth (Layer.py:1309-1334) + create_surficial_front (:1336-1416)
   {
     const bool needG = brA && c.st == 0;
-    double theta_1 = 0.0, theta_2 = 0.0;
+    R theta_1(0.0), theta_2(0.0);
     if (needG) {
-      theta_1 = C.f(F_THETA, 0);
-      theta_2 = C.soil[0].the;
+      theta_1 = C.g(F_THETA, 0);
+      theta_2 = R(C.soil[0].the);
     }
-    const double geff = geff_warp(needG, theta_1, theta_2, C.soil[0], nint, nodebuf, c);
+    const R geff = geff_warpR(needG, theta_1, theta_2, C.soil[0], nint, nodebuf, c);
     if (needG && c.st == 0) {
-      const Soil& s = C.soil[0];
-      const double cur_theta = C.f(F_THETA, 0);
-      const double delta_theta = s.the - cur_theta;
-      const double tau = dt * s.ksat / delta_theta;
-      double dry_depth = 0.5 * (tau + sqrt(tau * tau + 4.0 * tau * geff));
+      const SoilT<R>& s = C.soil[0];
+      const R cur_theta = C.g(F_THETA, 0);
+      const R delta_theta = s.the - cur_theta;
+      const R tau = dt * s.ksatR() / delta_theta;
+      R dry_depth = 0.5 * (tau + sqrt_(tau * tau + 4.0 * tau * geff));
       dry_depth = tmin(C.cum[0], dry_depth);
-      double theta_new;
+      R theta_new(0.0);
       bool to_bottom;
       if (dry_depth * delta_theta > ponded_depth_sub) {
         infiltration_sub = ponded_depth_sub;
         theta_new = tmin(cur_theta + ponded_depth_sub / dry_depth, s.the);
         to_bottom = false;
-        ponded_depth_sub = 0.0;
+        ponded_depth_sub = R(0.0);
       } else {
         infiltration_sub = dry_depth * delta_theta;
         ponded_depth_sub = ponded_depth_sub - (dry_depth * delta_theta);
-        theta_new = s.the;
+        theta_new = R(s.the);
         to_bottom = !(dry_depth < C.cum[0]);
       }
       if (C.insert_at(0, 0, c)) {
-        C.f(F_DEPTH, 0) = dry_depth;
-        C.f(F_THETA, 0) = theta_new;
+        C.s(F_DEPTH, 0, dry_depth);
+        C.s(F_THETA, 0, theta_new);
         C.set_flag(0, 0, to_bottom);
-        double se = se_from_theta(theta_new, s, c);
-        C.f(F_PSI, 0) = h_from_se(se, s, c);
-        C.f(F_K, 0) = k_from_se(se, s.ksat, s.m, s.inv_m, c) * K.p.frozen_factor;
-        C.f(F_DZDT, 0) = 0.0;
+        R se = se_thetaR(theta_new, s, c);
+        C.s(F_PSI, 0, h_seR(se, s, c));
+        C.s(F_K, 0, k_seR(se, s, c) * K.p.frozen_factor);
+        C.s(F_DZDT, 0, R(0.0));
       }
       T.acc[LGAR_OUT_INFILTRATION] = T.acc[LGAR_OUT_INFILTRATION] + infiltration_sub;
     }
@@ -259,12 +257,12 @@ __device__ void substep(Tile<FM>& T, bool act, double precip_rate, double pet_ra
   // update_ponded_depth (models/dpLGAR.py:369-382) for every lane that did not insert water
   if (act && !brB) {
     if (ponded_depth_sub < C.pdm) {
-      runoff_sub = 0.0;
+      runoff_sub = R(0.0);
       ponded_water_sub = ponded_depth_sub;
-      ponded_depth_sub = 0.0;
+      ponded_depth_sub = R(0.0);
     } else {
       runoff_sub = ponded_depth_sub - C.pdm;
-      ponded_depth_sub = C.pdm;
+      ponded_depth_sub = R(C.pdm);
       ponded_water_sub = ponded_depth_sub;
     }
     T.acc[LGAR_OUT_RUNOFF] = T.acc[LGAR_OUT_RUNOFF] + runoff_sub;
@@ -280,42 +278,42 @@ __device__ void substep(Tile<FM>& T, bool act, double precip_rate, double pet_ra
     int l = 0, o_next = go ? C.cnt(0) : 0;  // list layer of flat index i
     for (int i = 0; i < nmax; i++) {
       bool needG = false;
-      double theta_1 = 0.0, theta_2 = 0.0, bottom_sum = 0.0;
+      R theta_1(0.0), theta_2(0.0), bottom_sum(0.0);
       const bool mine = go && (i < my_n) && (c.st == 0);
       if (mine) {
         while (i >= o_next) {
           l++;
           o_next += C.cnt(l);
         }
-        theta_1 = C.f(F_THETA, i + 1);
-        theta_2 = C.f(F_THETA, i);
+        theta_1 = C.g(F_THETA, i + 1);
+        theta_2 = C.g(F_THETA, i);
         if (C.tb(i)) {
-          C.f(F_DZDT, i) = 0.0;
+          C.s(F_DZDT, i, R(0.0));
         } else {
           if (C.lay(i) > 0) {
             if (l == 0) raise(c, LGAR_ST_NULL_NEIGHBOUR);  // self.previous_layer is None
-            else bottom_sum = 0.0 + (C.f(F_DEPTH, i) - C.cum[l - 1]) / C.f(F_K, i);
+            else bottom_sum = 0.0 + (C.g(F_DEPTH, i) - C.cum[l - 1]) / C.g(F_K, i);
           } else if (theta_1 > theta_2) {
             raise(c, LGAR_ST_THETA_ORDER);
           }
           needG = (c.st == 0);
         }
       }
-      const double geff = geff_warp(needG, theta_1, theta_2, C.soil[needG ? l : 0], nint, nodebuf, c);
+      const R geff = geff_warpR(needG, theta_1, theta_2, C.soil[needG ? l : 0], nint, nodebuf, c);
       if (needG && c.st == 0) {
-        const Soil& s = C.soil[l];
-        const double depth = C.f(F_DEPTH, i);
-        const double delta_theta = theta_2 - theta_1;
-        double dzdt = 0.0;
+        const SoilT<R>& s = C.soil[l];
+        const R depth = C.g(F_DEPTH, i);
+        const R delta_theta = theta_2 - theta_1;
+        R dzdt(0.0);
         if (C.lay(i) == 0) {
           if (delta_theta > 0.0)
-            dzdt = 1.0 / delta_theta * (s.ksat * (geff + ponded_depth_sub) / depth + C.f(F_K, i));
+            dzdt = 1.0 / delta_theta * (s.ksatR() * (geff + ponded_depth_sub) / depth + C.g(F_K, i));
         } else {
-          const double denominator = C.calc_bottom_sum(0, bottom_sum, C.f(F_PSI, i), C.lay(i), c);
+          const R denominator = C.calc_bottom_sum(0, bottom_sum, C.g(F_PSI, i), C.lay(i), c);
           if (delta_theta > 0.0)
-            dzdt = (1.0 / delta_theta) * ((depth / denominator) + s.ksat * (geff + ponded_depth_sub) / depth);
+            dzdt = (1.0 / delta_theta) * ((depth / denominator) + s.ksatR() * (geff + ponded_depth_sub) / depth);
         }
-        C.f(F_DZDT, i) = dzdt;
+        C.s(F_DZDT, i, dzdt);
       }
     }
   }
@@ -329,12 +327,12 @@ __device__ void substep(Tile<FM>& T, bool act, double precip_rate, double pet_ra
     // GIUH (lgar/giuh.py:8-20, models/dpLGAR.py:292-298)
     const int ng = K.p.num_giuh;
     double qsum = 0.0;
-    for (int i = 0; i < ng; i++) qsum = qsum + C.giuh[i];
+    for (int i = 0; i < ng; i++) qsum = qsum + val(C.giuh[i]);
     if (qsum > 0.0 || runoff_sub > 0.0) {
       for (int i = 0; i < ng; i++) C.giuh[i] = C.giuh[i] + (K.p.giuh_ordinates[i] * runoff_sub);
-      const double now = C.giuh[0];
+      const R now = C.giuh[0];
       for (int i = 0; i + 1 < ng; i++) C.giuh[i] = C.giuh[i + 1];
-      C.giuh[ng - 1] = 0.0;
+      C.giuh[ng - 1] = R(0.0);
       T.acc[LGAR_OUT_GIUH_RUNOFF] = T.acc[LGAR_OUT_GIUH_RUNOFF] + now;
       T.acc[LGAR_OUT_DISCHARGE] = T.acc[LGAR_OUT_DISCHARGE] + now;
     }
@@ -345,20 +343,20 @@ __device__ void substep(Tile<FM>& T, bool act, double precip_rate, double pet_ra
 // state save / restore (global memory, column fastest).  Loads bypass L1 (__ldcg): the
 // record may have been written by a warp on another SM.
 // ------------------------------------------------------------------------------------
-template <int FM>
-__device__ void save_state(const KParams& K, int slot, int b, Tile<FM>& T) {
+template <int FM, class R>
+__device__ void save_state(const KParams& K, int slot, int b, Tile<FM, R>& T) {
   const size_t Bp = K.Bp;
   double* sd = K.state_d + (size_t)slot * state_doubles<FM>() * Bp + b;
-  Column<FM>& C = T.col;
+  Column<FM, R>& C = T.col;
   for (int i = 0; i < C.n; i++) {
 #pragma unroll
     for (int k = 0; k < 5; k++) sd[(size_t)(k * FM + i) * Bp] = C.f(k, i);
   }
   double* ss = sd + (size_t)(5 * FM) * Bp;
-  ss[(size_t)S_PONDED * Bp] = C.ponded_water;
+  ss[(size_t)S_PONDED * Bp] = val(C.ponded_water);
   ss[(size_t)S_PREV_PRECIP * Bp] = C.previous_precip;
-  ss[(size_t)S_END_VOL * Bp] = C.ending_volume;
-  for (int i = 0; i < NGIUH; i++) ss[(size_t)(S_GIUH + i) * Bp] = C.giuh[i];
+  ss[(size_t)S_END_VOL * Bp] = val(C.ending_volume);
+  for (int i = 0; i < NGIUH; i++) ss[(size_t)(S_GIUH + i) * Bp] = val(C.giuh[i]);
   for (int k = 0; k < NOUT; k++) ss[(size_t)(S_SUMS + k) * Bp] = T.sums[k];
   int32_t* si = K.state_i + (size_t)slot * NI_STATE * Bp + b;
   si[0] = C.n;
@@ -368,11 +366,11 @@ __device__ void save_state(const KParams& K, int slot, int b, Tile<FM>& T) {
   uint8_t* sf = K.state_f + (size_t)slot * FM * Bp + b;
   for (int i = 0; i < C.n; i++) sf[(size_t)i * Bp] = C.gb[i * NT];
 }
-template <int FM>
-__device__ void load_state(const KParams& K, int slot, int b, Tile<FM>& T) {
+template <int FM, class R>
+__device__ void load_state(const KParams& K, int slot, int b, Tile<FM, R>& T) {
   const size_t Bp = K.Bp;
   const double* sd = K.state_d + (size_t)slot * state_doubles<FM>() * Bp + b;
-  Column<FM>& C = T.col;
+  Column<FM, R>& C = T.col;
   const int32_t* si = K.state_i + (size_t)slot * NI_STATE * Bp + b;
   C.n = __ldcg(si);
   C.cntpk = (unsigned)__ldcg(si + Bp);
@@ -383,10 +381,10 @@ __device__ void load_state(const KParams& K, int slot, int b, Tile<FM>& T) {
     for (int k = 0; k < 5; k++) C.f(k, i) = __ldcg(sd + (size_t)(k * FM + i) * Bp);
   }
   const double* ss = sd + (size_t)(5 * FM) * Bp;
-  C.ponded_water = __ldcg(ss + (size_t)S_PONDED * Bp);
+  C.ponded_water = R(__ldcg(ss + (size_t)S_PONDED * Bp));
   C.previous_precip = __ldcg(ss + (size_t)S_PREV_PRECIP * Bp);
-  C.ending_volume = __ldcg(ss + (size_t)S_END_VOL * Bp);
-  for (int i = 0; i < NGIUH; i++) C.giuh[i] = __ldcg(ss + (size_t)(S_GIUH + i) * Bp);
+  C.ending_volume = R(__ldcg(ss + (size_t)S_END_VOL * Bp));
+  for (int i = 0; i < NGIUH; i++) C.giuh[i] = R(__ldcg(ss + (size_t)(S_GIUH + i) * Bp));
   for (int k = 0; k < NOUT; k++) T.sums[k] = __ldcg(ss + (size_t)(S_SUMS + k) * Bp);
   const uint8_t* sf = K.state_f + (size_t)slot * FM * Bp + b;
   for (int i = 0; i < C.n; i++) C.gb[i * NT] = __ldcg(sf + (size_t)i * Bp);
@@ -394,15 +392,15 @@ __device__ void load_state(const KParams& K, int slot, int b, Tile<FM>& T) {
 
 // load the column's parameters and derive the per-layer constants
 // (models/dpLGAR.py:41-57, data/utils.py:75-91 calc_m, GlobalParams.py:99-110)
-template <int FM>
-__device__ void load_params(const KParams& K, int b, Tile<FM>& T) {
+template <int FM, class R>
+__device__ void load_params(const KParams& K, int b, Tile<FM, R>& T) {
   const lgar_problem& p = K.p;
-  Column<FM>& C = T.col;
+  Column<FM, R>& C = T.col;
   const size_t B = p.num_columns;
   C.L = p.num_layers;
   double cumv = 0.0;
   for (int l = 0; l < C.L; l++) {
-    Soil& s = C.soil[l];
+    SoilT<R>& s = C.soil[l];
     s.alpha = __ldg(p.alpha + l * B + b);
     s.n = __ldg(p.n + l * B + b);
     s.ksat = __ldg(p.ksat + l * B + b);
@@ -437,8 +435,9 @@ __global__ void __launch_bounds__(NT) lgar_forward_kernel(const KParams K) {
   const size_t B = p.num_columns;
   const unsigned long long nitems = (unsigned long long)K.ntiles * K.nchunks;
 
-  Tile<FM> T;
+  Tile<FM, double> T;
   T.col.fb = sm_fields + threadIdx.x;
+  T.col.ib = nullptr;
   T.col.gb = sm_flags + threadIdx.x;
   T.ctx.iter_cap = K.iter_cap;
 
