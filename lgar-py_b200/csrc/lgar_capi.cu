@@ -76,6 +76,18 @@ Carve carve(const Shape& s, int with_grad) {
 int g_dev_checked = -2;
 int g_num_sms = 0;
 
+// reverse kernel: resident warps that own scratch (ring, tape, adjoints).  Sized without a device
+// query so that lgar_workspace_bytes works on a host without a GPU: <= 160 SMs, CTAs per SM bounded by
+// the shared-memory footprint of the value + id arrays.
+#define LGAR_TAPE_CAP 6144
+int backward_ctas_per_sm(const Shape& s) { return s.FM == 16 ? 1 : (s.FM == 12 ? 2 : 3); }
+int backward_slots(const Shape& s) {
+  long long want = ((long long)s.ntiles + lgar::WARPS - 1) / lgar::WARPS;
+  long long grid = 160LL * backward_ctas_per_sm(s);
+  if (grid > want) grid = want;
+  return (int)grid * lgar::WARPS;
+}
+
 template <int FM>
 size_t smem_bytes() {
   return (size_t)5 * FM * lgar::NT * sizeof(double) + (size_t)lgar::WARPS * lgar::NODEBUF * sizeof(double) +
@@ -133,6 +145,42 @@ struct DevBuf {
 }  // namespace
 
 
+#ifdef LGAR_WITH_BACKWARD
+namespace {
+template <int FM>
+int launch_backward(lgar::BParams& P, const Shape& s, unsigned char* scratch, cudaStream_t st) {
+  auto kern = lgar::lgar_backward_kernel<FM>;
+  const size_t smem = (size_t)5 * FM * lgar::NT * sizeof(double) + (size_t)lgar::WARPS * lgar::NODEBUF * sizeof(double) +
+                      (size_t)5 * FM * lgar::NT * sizeof(int) + (size_t)FM * lgar::NT;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, lgar::NT, smem));
+  if (per_sm < 1) return fail(LGAR_E_CUDA, "backward kernel does not fit on an SM");
+  const int slots = backward_slots(s);
+  long long grid = (long long)g_num_sms * per_sm;
+  if (grid > slots / lgar::WARPS) grid = slots / lgar::WARPS;
+  if (grid < 1) grid = 1;
+  const size_t ring_steps = (size_t)s.chunk * s.S;
+  const size_t nd = 5 * (size_t)FM + lgar::S_SUMS, nl = lgar::num_leaves<FM>();
+  size_t o = 0;
+  auto take = [&](size_t bytes) { unsigned char* q = scratch + o; o += (bytes + 255) / 256 * 256; return q; };
+  P.ring_d = (double*)take((size_t)slots * ring_steps * nd * 32 * 8);
+  P.ring_i = (int32_t*)take((size_t)slots * ring_steps * 2 * 32 * 4);
+  P.ring_f = (uint8_t*)take((size_t)slots * ring_steps * FM * 32);
+  P.tape = (lgar::TapeEntry*)take((size_t)slots * LGAR_TAPE_CAP * 32 * sizeof(lgar::TapeEntry));
+  P.adj = (double*)take((size_t)slots * (nl + LGAR_TAPE_CAP) * 32 * 8);
+  P.lam = (double*)take((size_t)slots * nl * 32 * 8);
+  P.next_tile = (unsigned long long*)take(64);
+  P.ring_steps = (int32_t)ring_steps;
+  P.tape_cap = LGAR_TAPE_CAP;
+  CUDA_TRY(cudaMemsetAsync(P.next_tile, 0, 64, st));
+  kern<<<(unsigned)grid, lgar::NT, smem, st>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+}  // namespace
+#endif
+
 extern "C" {
 
 int lgar_abi_version(void) { return LGAR_ABI_VERSION; }
@@ -157,7 +205,8 @@ size_t lgar_workspace_bytes(const lgar_problem* p, int with_grad) {
   if (shape_of(p, s)) return 0;
   size_t total = carve(s, with_grad).total;
 #ifdef LGAR_WITH_BACKWARD
-  if (with_grad) total += lgar::backward_scratch_bytes(s.B, s.Bp, s.L, s.S, s.FM, s.chunk);
+  if (with_grad)
+    total += lgar::backward_scratch_bytes(s.B, s.Bp, s.L, s.S, s.FM, s.chunk, backward_slots(s), LGAR_TAPE_CAP);
 #endif
   return total;
 }
@@ -214,6 +263,52 @@ int lgar_forward(const lgar_problem* p, const lgar_outputs* out, void* workspace
 #undef LGAR_DISPATCH
   return rc;
 }
+
+#ifdef LGAR_WITH_BACKWARD
+int lgar_backward(const lgar_problem* p, const double* grad_per_step, uint32_t grad_mask, const double* grad_sums,
+                  double* grad_alpha, double* grad_n, double* grad_ksat, void* workspace_dev, size_t workspace_bytes,
+                  void* stream) {
+  Shape s;
+  int rc = shape_of(p, s);
+  if (rc) return rc;
+  if (!grad_alpha || !grad_n || !grad_ksat) return fail(LGAR_E_INVALID, "gradient output array is NULL");
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev != g_dev_checked) {
+    rc = lgar_device_check();
+    if (rc) return rc;
+  }
+  const Carve c = carve(s, 1);
+  const size_t need = lgar_workspace_bytes(p, 1);
+  if (!workspace_dev || workspace_bytes < need) return fail(LGAR_E_WORKSPACE, "workspace too small for lgar_backward");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* w = (unsigned char*)workspace_dev;
+  lgar::BParams P;
+  std::memset(&P, 0, sizeof(P));
+  lgar::KParams& K = P.K;
+  K.p = *p;
+  K.state_d = (double*)(w + c.off_d);
+  K.state_i = (int32_t*)(w + c.off_i);
+  K.state_f = (uint8_t*)(w + c.off_f);
+  K.done = (int32_t*)(w + c.off_done);
+  K.next_item = (unsigned long long*)(w + c.off_item);
+  K.Bp = s.Bp;
+  K.ntiles = s.ntiles;
+  K.nchunks = s.nchunks;
+  K.chunk_steps = s.chunk;
+  K.keep_ckpt = 1;
+  K.iter_cap = p->iter_cap > 0 ? p->iter_cap : 1000000;
+  P.grad_per_step = grad_per_step;
+  P.grad_mask = grad_per_step ? grad_mask : 0;
+  P.grad_sums = grad_sums;
+  P.grad_alpha = grad_alpha;
+  P.grad_n = grad_n;
+  P.grad_ksat = grad_ksat;
+  unsigned char* scratch = w + c.total;
+  if (s.FM == 8) return launch_backward<8>(P, s, scratch, st);
+  if (s.FM == 12) return launch_backward<12>(P, s, scratch, st);
+  return launch_backward<16>(P, s, scratch, st);
+}
+#endif
 
 #ifndef LGAR_WITH_BACKWARD
 int lgar_backward(const lgar_problem*, const double*, uint32_t, const double*, double*, double*, double*, void*,
