@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--columns", type=int, default=125_000, help="columns per GPU")
@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--cpu-sample-columns", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--grad-columns", type=int, default=16384,
+                    help="columns of the shard used for the forward+gradient figure (0 = skip)")
     return ap.parse_args()
 
 
@@ -163,7 +165,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # one counting pass (untimed): work counters -> algorithmic flop per launch, alive column-steps
+    # the first warm-up pass also counts closure calls (work counters -> algorithmic flop per launch)
+    # and tells how many column-steps are actually simulated (crashed columns stop at their crash step)
     res, ws = forward_raw(ens, d_alpha, d_n, d_ksat, outputs=outs, counters=True)
     torch.cuda.synchronize()
     counters = res.counters.cpu().numpy()
@@ -178,7 +181,7 @@ def main():
         r, _ = forward_raw(ens, d_alpha, d_n, d_ksat, outputs=outs, workspace=ws)
         return r
 
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup - 1, 0)):
         one_pass()
     barrier()
     sampler = ClockSampler(local)
@@ -204,7 +207,7 @@ def main():
             k = host["ksat"].to(dev, non_blocking=True)
             r, _ = forward_raw(ens, a, n_, k, outputs=outs, workspace=ws)
             return r.sums.cpu(), r.status.cpu()
-        e2e_pass()
+        e2e_pass()  # one warm-up of the host path (pinned staging buffers, allocator)
         barrier()
         t0 = time.perf_counter()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -218,15 +221,47 @@ def main():
         d2h = sums_h.numel() * 8 + st_h.numel() * 4
         e2e = (e2e_ms, h2d, d2h)
 
-    stats = torch.tensor([total_ms, float(alive_steps), flop_per_launch, e2e[0] if e2e else 0.0],
-                         dtype=torch.float64, device=dev)
+    # forward + gradient (reverse-mode kernel) on the first `grad_columns` columns of the shard, full record
+    fg = None
+    if args.grad_columns > 0:
+        from lgar_b200 import lgar_columns
+        Bg = min(args.grad_columns, B)
+        del ws
+        torch.cuda.empty_cache()
+        sub = lambda x: np.ascontiguousarray(x[:, :Bg])
+        ens_g = ColumnEnsemble(theta_r=sub(we.theta_r), theta_e=sub(we.theta_e), thickness=sub(we.thickness),
+                               forcing=we.forcing, site_index=we.site_index[:Bg], max_fronts=args.max_fronts,
+                               chunk_steps=args.chunk, device=dev)
+        alive_g = int(np.where(status[:Bg] == 0, T, np.maximum(crash[:Bg], 0)).sum())
+
+        def fwd_bwd():
+            A = d_alpha[:, :Bg].clone().requires_grad_(True)
+            N_ = d_n[:, :Bg].clone().requires_grad_(True)
+            Kk = d_ksat[:, :Bg].clone().requires_grad_(True)
+            out = lgar_columns(A, N_, Kk, ens_g, outputs=("runoff", "AET"))
+            ok = out["status"] == 0
+            loss = torch.nan_to_num(out["runoff"] + out["AET"]).sum(dim=0)[ok].mean()
+            loss.backward()
+            return A.grad
+        fwd_bwd()
+        barrier()
+        g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
+        g0.record()
+        grad = fwd_bwd()
+        g1.record()
+        barrier()
+        fg = (g0.elapsed_time(g1), alive_g, float(torch.isfinite(grad).float().mean()))
+
+    stats = torch.tensor([total_ms, float(alive_steps), flop_per_launch, e2e[0] if e2e else 0.0,
+                          fg[0] if fg else 0.0, float(fg[1]) if fg else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        total_ms, e2e_ms_all = float(mx[0]), float(mx[3])
-        alive_all, flop_all = float(sm[1]), float(sm[2])
+        total_ms, e2e_ms_all, fg_ms_all = float(mx[0]), float(mx[3]), float(mx[4])
+        alive_all, flop_all, fg_alive_all = float(sm[1]), float(sm[2]), float(sm[5])
     else:
         e2e_ms_all, alive_all, flop_all = float(stats[3]), float(alive_steps), flop_per_launch
+        fg_ms_all, fg_alive_all = float(stats[4]), float(stats[5])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -262,6 +297,12 @@ def main():
                      "hbm": {"algorithmic_bytes_per_launch": out_bytes, "achieved_gbs": out_bytes / kern_s / 1e9,
                              "peak_gbs": hbm_peak, "frac": out_bytes / kern_s / 1e9 / hbm_peak}},
     }
+    if fg:
+        line["fwd_grad"] = {"value": fg_alive_all / (fg_ms_all * 1e-3), "unit": "column-timesteps/s",
+                            "columns_per_gpu": min(args.grad_columns, B), "forcing_steps": T,
+                            "what": "lgar_forward(keep checkpoints) + lgar_backward through torch.autograd, "
+                                    "loss = mean over OK columns of sum_t (runoff + AET); bounded column subset of the "
+                                    "same shard, full record", "finite_grad_fraction": fg[2]}
     if e2e:
         line["e2e"] = {"value": alive_all / (e2e_ms_all / args.steps * 1e-3), "unit": "column-timesteps/s",
                        "h2d_bytes_per_step": e2e[1], "d2h_bytes_per_step": e2e[2]}

@@ -95,6 +95,11 @@ typedef struct lgar_problem {
   int32_t num_giuh;        /* <= LGAR_MAX_GIUH               cfg.data.giuh_ordinates            */
   int32_t max_fronts;      /* 8, 12 or 16 (0 = 16): front-list capacity per column              */
   int32_t chunk_steps;     /* forcing steps per scheduling/checkpoint chunk (0 = default 64)    */
+  int32_t resume;          /* 0: start from set_internal_states() (models/dpLGAR.py:97-147);
+                              1: continue from the column state the previous lgar_forward left in
+                              this workspace (same B, L, max_fronts; keep_checkpoints == 0): lets a
+                              caller advance one forcing row per call like dpLGAR.forward(x)         */
+  int32_t reserved1;
   int64_t iter_cap;        /* root-finder iteration cap (0 = default 1,000,000)                 */
   double subcycle_length_h;   /* dt in hours                 cfg.models.subcycle_length_h       */
   double wilting_point_psi;   /* cm                          cfg.data.wilting_point_psi         */

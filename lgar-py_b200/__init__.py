@@ -8,6 +8,8 @@ Public surface:
 from . import _capi
 from ._capi import OUT_NAMES, STATUS_NAMES, LGARLibraryError
 from .columns import ColumnEnsemble, ForwardResult, forward_raw, lgar_columns, output_mask
+from .model import dpLGAR
+from . import parallel, workloads
 
 __all__ = ["ColumnEnsemble", "ForwardResult", "forward_raw", "lgar_columns", "output_mask", "OUT_NAMES",
-           "STATUS_NAMES", "LGARLibraryError", "_capi"]
+           "STATUS_NAMES", "LGARLibraryError", "dpLGAR", "parallel", "workloads", "_capi"]

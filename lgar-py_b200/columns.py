@@ -55,6 +55,7 @@ class ColumnEnsemble:
     max_fronts: int = 16
     chunk_steps: int = 64
     iter_cap: int = 0
+    resume: bool = False             # continue from the state left in the workspace (see lgar_b200.h)
     device: object = "cuda"
     _keep: list = field(default_factory=list, repr=False)
 
@@ -92,6 +93,7 @@ class ColumnEnsemble:
         p.num_subcycles, p.num_sites = int(self.num_subcycles), self.forcing.shape[0]
         p.nint, p.num_giuh = int(self.nint), len(self.giuh_ordinates)
         p.max_fronts, p.chunk_steps, p.iter_cap = int(self.max_fronts), int(self.chunk_steps), int(self.iter_cap)
+        p.resume = 1 if self.resume else 0
         p.subcycle_length_h = float(self.subcycle_length_h)
         p.wilting_point_psi = float(self.wilting_point_psi)
         p.frozen_factor = float(self.frozen_factor)

@@ -221,6 +221,7 @@ int lgar_forward(const lgar_problem* p, const lgar_outputs* out, void* workspace
       !p->ponded_depth_max || !p->forcing)
     return fail(LGAR_E_INVALID, "a required problem array is NULL");
   if (p->num_sites < 1) return fail(LGAR_E_INVALID, "num_sites < 1");
+  if (p->resume && keep_checkpoints) return fail(LGAR_E_INVALID, "resume is not available with keep_checkpoints");
   int dev = -1;
   if (cudaGetDevice(&dev) != cudaSuccess || dev != g_dev_checked) {
     rc = lgar_device_check();

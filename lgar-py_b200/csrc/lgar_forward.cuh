@@ -467,7 +467,10 @@ __global__ void __launch_bounds__(NT) lgar_forward_kernel(const KParams K) {
     const long long clk0 = clock64();
     load_params(K, bb, T);
     const int slot_in = K.keep_ckpt ? chunk : 0;
-    if (chunk == 0) {
+    if (chunk == 0 && p.resume) {
+      load_state(K, 0, bb, T);  // continue from the state the previous launch left in the workspace
+      if (T.crash_step >= 0) T.crash_step = -2 - T.crash_step;  // crashed in an earlier call
+    } else if (chunk == 0) {
       T.ctx.st = 0;
       T.crash_step = -1;
       init_column(T, __ldg(p.initial_psi + bb));

@@ -1,0 +1,29 @@
+"""Time-boxed timing of forward(keep checkpoints) + backward for a (columns x steps) shape."""
+import sys, os, time
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import lgar_b200
+from lgar_b200 import workloads, ColumnEnsemble, lgar_columns
+shapes = [tuple(int(x) for x in a.split("x")) for a in sys.argv[1:]] or [(2048, 256)]
+for B, T in shapes:
+    we = workloads.synthetic_sites_ensemble(B=B, T=T, sites=max(1, min(128, B // 32)), rank=0)
+    ens = ColumnEnsemble(theta_r=we.theta_r, theta_e=we.theta_e, thickness=we.thickness, forcing=we.forcing,
+                         site_index=we.site_index, chunk_steps=int(os.environ.get("LGAR_DIAG_CHUNK", "64")))
+    for rep in range(2):
+        A = torch.tensor(we.alpha, device="cuda", requires_grad=True)
+        N = torch.tensor(we.n, device="cuda", requires_grad=True)
+        K = torch.tensor(we.ksat, device="cuda", requires_grad=True)
+        torch.cuda.synchronize(); e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        out = lgar_columns(A, N, K, ens, outputs=("runoff", "AET"))
+        e[1].record()
+        ok = out["status"] == 0
+        loss = torch.nan_to_num(out["runoff"] + out["AET"]).sum(dim=0)[ok].mean()
+        loss.backward()
+        e[2].record(); torch.cuda.synchronize()
+    st = out["status"].cpu().numpy(); cr = out["crash_step"].cpu().numpy()
+    alive = int(np.where(st == 0, T, np.maximum(cr, 0)).sum())
+    f, b = e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
+    gn = A.grad[:, ok]
+    print(f"B={B} T={T}: fwd {f:.0f} ms, bwd {b:.0f} ms -> fwd+grad {alive/(f+b)*1e3:.4g} col-steps/s (fwd alone {alive/f*1e3:.4g}); "
+          f"grad finite frac {float(torch.isfinite(gn).float().mean()):.4f}  |dL/dalpha0| mean {float(gn[0].abs().nanmean()):.3g}", flush=True)
