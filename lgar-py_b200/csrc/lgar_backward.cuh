@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(NT) lgar_backward_kernel(const BParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sm_fields = reinterpret_cast<double*>(smem_raw);                       // [5*FM][NT]
   double* sm_nodes = sm_fields + 5 * FM * NT;                                    // [WARPS][NODEBUF]
-  int* sm_ids = reinterpret_cast<int*>(sm_nodes + WARPS * NODEBUF);              // [5*FM][NT]
+  short* sm_ids = reinterpret_cast<short*>(sm_nodes + WARPS * NODEBUF);          // [5*FM][NT]
   uint8_t* sm_flags = reinterpret_cast<uint8_t*>(sm_ids + 5 * FM * NT);          // [FM][NT]
   __shared__ unsigned long long sm_item[WARPS];
 

@@ -79,8 +79,8 @@ int g_num_sms = 0;
 // reverse kernel: resident warps that own scratch (ring, tape, adjoints).  Sized without a device
 // query so that lgar_workspace_bytes works on a host without a GPU: <= 160 SMs, CTAs per SM bounded by
 // the shared-memory footprint of the value + id arrays.
-#define LGAR_TAPE_CAP 6144
-int backward_ctas_per_sm(const Shape& s) { return s.FM == 16 ? 1 : (s.FM == 12 ? 2 : 3); }
+#define LGAR_TAPE_CAP 6144  /* + leaves must stay below 32768: ids are stored as 16 bit in shared memory */
+int backward_ctas_per_sm(const Shape& s) { return s.FM == 16 ? 2 : (s.FM == 12 ? 2 : 4); }
 int backward_slots(const Shape& s) {
   long long want = ((long long)s.ntiles + lgar::WARPS - 1) / lgar::WARPS;
   long long grid = 160LL * backward_ctas_per_sm(s);
@@ -151,7 +151,7 @@ template <int FM>
 int launch_backward(lgar::BParams& P, const Shape& s, unsigned char* scratch, cudaStream_t st) {
   auto kern = lgar::lgar_backward_kernel<FM>;
   const size_t smem = (size_t)5 * FM * lgar::NT * sizeof(double) + (size_t)lgar::WARPS * lgar::NODEBUF * sizeof(double) +
-                      (size_t)5 * FM * lgar::NT * sizeof(int) + (size_t)FM * lgar::NT;
+                      (size_t)5 * FM * lgar::NT * sizeof(short) + (size_t)FM * lgar::NT;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, lgar::NT, smem));

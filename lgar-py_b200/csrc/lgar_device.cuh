@@ -617,7 +617,7 @@ template <int FM, class R>
 struct Column {
   static constexpr bool TAPED = !std::is_same<R, double>::value;
   double* fb;        // this thread's slot in the field array
-  int* ib;           // this thread's slot in the id array (TAPED only)
+  short* ib;         // this thread's slot in the 16-bit tape-id array (TAPED only; ids < 32768)
   uint8_t* gb;       // this thread's slot in the flag array: bits 0-2 layer_num attr, bit 7 to_bottom
   int L;             // number of layers
   int n;             // total number of fronts
@@ -633,16 +633,16 @@ struct Column {
   bool empty_list;   // set by mass_balance() when a layer list is empty (IndexError in the reference)
 
   __device__ __forceinline__ double& f(int fld, int i) { return fb[(fld * FM + i) * NT]; }
-  __device__ __forceinline__ int& fid(int fld, int i) { return ib[(fld * FM + i) * NT]; }
+  __device__ __forceinline__ short& fid(int fld, int i) { return ib[(fld * FM + i) * NT]; }
   // generic get / set of a field as R
   __device__ __forceinline__ R g(int fld, int i) {
-    if constexpr (TAPED) return Var(f(fld, i), fid(fld, i));
+    if constexpr (TAPED) return Var(f(fld, i), (int)fid(fld, i));
     else return f(fld, i);
   }
   __device__ __forceinline__ void s(int fld, int i, const R& x) {
     if constexpr (TAPED) {
       f(fld, i) = x.v;
-      fid(fld, i) = x.id;
+      fid(fld, i) = (short)x.id;
     } else {
       f(fld, i) = x;
     }
