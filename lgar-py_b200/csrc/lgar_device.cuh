@@ -242,7 +242,7 @@ __device__ __forceinline__ double2 h_from_se_x2(double se0, double se1, const So
 // visiting exactly the psi values the reference's `psi = psi +/- 0.1*factor` loop visits.
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ int f64_exponent(double x) { return (__double2hiint(x) >> 20) & 0x7ff; }
-__device__ double advance_rounded_pos(double x, double s, long long k) {
+__device__ __noinline__ double advance_rounded_pos(double x, double s, long long k) {
   while (k > 0) {
     const double t = x + s;
     k--;
@@ -295,12 +295,19 @@ __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync
 //            nodes j, j+32, j+64, ...
 //   stage C (requesting lane): geff = sum_i (K_{i-1} + K_i) * (dh / 2) in the reference's order.
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ double geff_warp(bool need, double theta_1, double theta_2, const Soil& s, int nint,
-                                         double* nodebuf, Ctx& c) {
+struct GeffRet {
+  double v;
+  int st;
+};
+// Out of line, arguments by value: one copy of the code for the three call sites of a sub-step, and
+// neither the status block nor the soil parameters are forced into local memory by the call.
+__device__ __noinline__ GeffRet geff_warp_core(bool need, double theta_1, double theta_2, Soil s, int nint,
+                                               double* nodebuf) {
+  Ctx c;
+  c.st = 0;
   const int lane = threadIdx.x & 31;
   double h_i = 0.0, dh = 0.0, k0 = 0.0;
   if (need) {
-    c.cnt[C_GEFF]++;
     double se_i = se_from_theta(theta_1, s, c);
     double se_f = se_from_theta(theta_2, s, c);
     const double2 hh = h_from_se_x2(se_i, se_f, s, c);
@@ -372,8 +379,6 @@ __device__ __forceinline__ double geff_warp(bool need, double theta_1, double th
     __syncwarp();
     if (lane == src) {
       if (st_any) raise(c, st_any);
-      c.cnt[C_SE_H] += nint;
-      c.cnt[C_K_SE] += nint;
       const double half = qdh / 2.0;
       double geff = 0.0;
       double k1 = nodebuf[0];
@@ -387,7 +392,22 @@ __device__ __forceinline__ double geff_warp(bool need, double theta_1, double th
     }
     __syncwarp();
   }
-  return result;
+  GeffRet r;
+  r.v = result;
+  r.st = c.st;
+  return r;
+}
+__device__ __forceinline__ double geff_warp(bool need, double theta_1, double theta_2, const Soil& s, int nint,
+                                            double* nodebuf, Ctx& c) {
+  const GeffRet r = geff_warp_core(need, theta_1, theta_2, s, nint, nodebuf);
+  if (need) {
+    c.cnt[C_GEFF]++;
+    c.cnt[C_H_SE] += 2;
+    c.cnt[C_K_SE] += 1 + nint;
+    c.cnt[C_SE_H] += nint;
+    if (r.st) raise(c, r.st);
+  }
+  return r.v;
 }
 
 // ------------------------------------------------------------------------------------
