@@ -9,7 +9,7 @@ from . import _capi
 from ._capi import OUT_NAMES, STATUS_NAMES, LGARLibraryError
 from .columns import ColumnEnsemble, ForwardResult, forward_raw, lgar_columns, output_mask
 from .model import dpLGAR
-from . import parallel, workloads
+from . import forcing, parallel, workloads
 
 __all__ = ["ColumnEnsemble", "ForwardResult", "forward_raw", "lgar_columns", "output_mask", "OUT_NAMES",
-           "STATUS_NAMES", "LGARLibraryError", "dpLGAR", "parallel", "workloads", "_capi"]
+           "STATUS_NAMES", "LGARLibraryError", "dpLGAR", "forcing", "parallel", "workloads", "_capi"]
