@@ -1009,6 +1009,11 @@ struct Column {
         bool run_up = false;
         long long stride = 0;   // > 0: next pass is a probe `stride` steps ahead
         bool shrinking = false;
+        // predictive probe: after the single up-step that ends a decade, the next down-run (10x finer step)
+        // needs k <= 10 steps to cross again; k is estimated by the secant through the last two evaluations
+        // and the lane probes k-1 steps ahead at once.  Acceptance is the same exact test as for galloping
+        // probes, so a wrong estimate only costs one evaluation.
+        bool pred = false;
         while (__any_sync(FULL, active)) {
           if (active) {
             if (it > c.iter_cap) {
@@ -1026,7 +1031,8 @@ struct Column {
             bool sw = switched;
             double fac = factor;
             if (probe) {
-              step = 0.1 * factor;
+              if (pred) fac = factor * 0.1;  // the first step of a down-run after an up-step shrinks the factor
+              step = 0.1 * fac;
               psi_try = advance_rounded(psi_cm, up ? step : -step, stride);
               if (!up) psi_prev_try = advance_rounded(psi_cm, -step, stride - 1);
               if (!up) prev_scale_try = psi_scale;
@@ -1084,16 +1090,28 @@ struct Column {
                 delta_mass_prev = dm;
                 count_no_mass_change = 0;
                 it += stride;
-                stride = shrinking ? (stride >> 1) : (stride << 1);
-                if (stride > (1LL << 40)) stride = 1LL << 40;
+                if (pred) {  // the run has started: factor was shrunk by its first step
+                  switched = true;
+                  factor = fac;
+                  run_len = 1;
+                  run_up = false;
+                  stride = 0;
+                } else {
+                  stride = shrinking ? (stride >> 1) : (stride << 1);
+                  if (stride > (1LL << 40)) stride = 1LL << 40;
+                }
+              } else if (pred) {
+                stride = 0;  // estimate too optimistic: step normally
               } else {
                 shrinking = true;
                 stride >>= 1;
               }
+              pred = false;
               if (stride < 2) stride = 0;
             } else {
               it++;
               if (cc.st) raise(c, cc.st);  // the reference raised inside theta_from_h
+              const double psi_a = psi_cm, mass_a = new_mass;  // previous evaluation (for the secant estimate)
               if (up == run_up && fac == factor) run_len++;
               else {
                 run_len = 1;
@@ -1124,6 +1142,18 @@ struct Column {
                 stride = 4;
                 shrinking = false;
                 run_len = 0;  // re-armed after three more regular steps of the same run
+              } else if (up && !(new_mass > prior_mass) && mass_layers != mass_a) {
+                // an up-step just crossed below prior_mass: the next iteration starts a down-run with step s2
+                const double s2 = 0.1 * (factor * 0.1);
+                const double psi_star = psi_cm - (mass_layers - prior_mass) * (psi_cm - psi_a) / (mass_layers - mass_a);
+                const double kest = (psi_cm - psi_star) / s2;
+                // (skip when one fine step changes the mass by less than the probe's monotonicity margin)
+                if (kest >= 3.0 && kest <= 4096.0 && psi_cm > 128.0 * s2 && fabs(mass_layers - mass_a) >= 4e-11) {
+                  stride = (long long)kest - 1;  // one step of margin before the estimated crossing
+                  pred = true;
+                  run_up = false;
+                  shrinking = false;
+                }
               }
             }
           }

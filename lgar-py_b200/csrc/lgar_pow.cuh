@@ -45,6 +45,23 @@ __device__ const PowExpEntry g_pow_exp_table[LGAR_POW_N] = {LGAR_POW_EXP_TABLE};
 static const PowLogEntry h_pow_log_table[LGAR_POW_N] = {LGAR_POW_LOG_TABLE};
 static const PowExpEntry h_pow_exp_table[LGAR_POW_N] = {LGAR_POW_EXP_TABLE};
 
+// Scalar constants.  On the device they live in __constant__ memory so that FP64 instructions take them as
+// constant-bank operands instead of materialising each 64-bit immediate with two moves.
+enum PowConst { PC_LN2HI, PC_LN2LO, PC_INVLN2N, PC_LN2N_HI, PC_LN2N_LO, PC_A3, PC_A4, PC_A5, PC_A6, PC_A7, PC_A8, PC_A9,
+                PC_C2, PC_C3, PC_C4, PC_C5, PC_C6, PC_SHIFT, PC_COUNT };
+#define LGAR_POW_CONSTS {LGAR_LN2HI, LGAR_LN2LO, LGAR_INVLN2N, -LGAR_LN2N_HI, -LGAR_LN2N_LO, LGAR_LOG_A3, LGAR_LOG_A4, \
+                         LGAR_LOG_A5, LGAR_LOG_A6, LGAR_LOG_A7, LGAR_LOG_A8, LGAR_LOG_A9, LGAR_EXP_C2, LGAR_EXP_C3, \
+                         LGAR_EXP_C4, LGAR_EXP_C5, LGAR_EXP_C6, 0x1.8p52}
+#ifdef __CUDACC__
+__constant__ double c_pow_consts[PC_COUNT] = LGAR_POW_CONSTS;
+#endif
+static const double h_pow_consts[PC_COUNT] = LGAR_POW_CONSTS;
+#ifdef __CUDA_ARCH__
+#define PCK(i) c_pow_consts[i]
+#else
+#define PCK(i) h_pow_consts[i]
+#endif
+
 LGAR_HD uint64_t pow_bits(double x) {
 #ifdef __CUDA_ARCH__
   return (uint64_t)__double_as_longlong(x);
@@ -77,7 +94,7 @@ LGAR_HD double pow_core(double x, double y, bool& ok) {
   // ---- log(x) = hi + lo
   const uint64_t tmp = ix - LGAR_POW_OFF;
   const int i = (int)((tmp >> 45) & (LGAR_POW_N - 1));
-  const int64_t k = (int64_t)tmp >> 52;
+  const int k = (int)((int64_t)tmp >> 52);
   const double z = pow_from_bits(ix - (tmp & 0xfff0000000000000ULL));
   const double kd = (double)k;
 #ifdef __CUDA_ARCH__
@@ -90,12 +107,11 @@ LGAR_HD double pow_core(double x, double y, bool& ok) {
   const double p = z * invc;
   const double rl = pow_fma(z, invc, -p);  // exact: z*invc = p + rl
   const double r = p - 1.0;                // exact (Sterbenz)
-  const double t1 = pow_fma(kd, LGAR_LN2HI, logc);  // exact: both are multiples of 2^-42 below 2^10
-  // TwoSum t1 + r
+  const double t1 = pow_fma(kd, PCK(PC_LN2HI), logc);  // exact: both are multiples of 2^-42 below 2^10
+  // Fast2Sum t1 + r: exact because t1 == 0 (interval 64, k = 0) or |t1| >= |log c_63| = 0.0059 > |r|
   const double t2 = t1 + r;
-  const double bb = t2 - t1;
-  const double lo2 = (t1 - (t2 - bb)) + (r - bb);
-  const double lo1 = pow_fma(kd, LGAR_LN2LO, logctail);
+  const double lo2 = (t1 - t2) + r;
+  const double lo1 = pow_fma(kd, PCK(PC_LN2LO), logctail);
   // -r^2/2 in two terms
   const double ar = -0.5 * r;
   const double ar2 = r * ar;
@@ -103,16 +119,16 @@ LGAR_HD double pow_core(double x, double y, bool& ok) {
   const double hi = t2 + ar2;
   const double lo4 = (t2 - hi) + ar2;
   const double r2 = r * r;
-  double q = pow_fma(r, LGAR_LOG_A10, LGAR_LOG_A9);
-  q = pow_fma(r, q, LGAR_LOG_A8);
-  q = pow_fma(r, q, LGAR_LOG_A7);
-  q = pow_fma(r, q, LGAR_LOG_A6);
-  q = pow_fma(r, q, LGAR_LOG_A5);
-  q = pow_fma(r, q, LGAR_LOG_A4);
-  q = pow_fma(r, q, LGAR_LOG_A3);
+  // log1p(r) - r + r^2/2 = r^3 (A3 + A4 r + ... + A9 r^6): |r| <= 0.0046, truncation < 2^-70 relative
+  double q = pow_fma(r, PCK(PC_A9), PCK(PC_A8));
+  q = pow_fma(r, q, PCK(PC_A7));
+  q = pow_fma(r, q, PCK(PC_A6));
+  q = pow_fma(r, q, PCK(PC_A5));
+  q = pow_fma(r, q, PCK(PC_A4));
+  q = pow_fma(r, q, PCK(PC_A3));
   const double pl = (r2 * r) * q;
   // contribution of the product rounding error rl: rl * d/dr log1p(r) = rl (1 - r + r^2)
-  const double lo5 = rl * (1.0 - r + r2);
+  const double lo5 = pow_fma(rl, r2 - r, rl);
   const double lo = ((lo1 + lo2) + (lo3 + lo4)) + (pl + lo5);
   const double lhi = hi + lo;
   const double llo = (hi - lhi) + lo;
@@ -123,11 +139,11 @@ LGAR_HD double pow_core(double x, double y, bool& ok) {
   const double aeh = ehi < 0.0 ? -ehi : ehi;
   ok = x_ok && (aeh < 700.0);
   // ---- exp(ehi + elo)
-  const double zz = ehi * LGAR_INVLN2N;
-  const double kf = (zz + 0x1.8p52) - 0x1.8p52;  // rint(zz), |zz| < 2^17
-  const int64_t ki = ok ? (int64_t)kf : 0;
-  double rr = pow_fma(kf, -LGAR_LN2N_HI, ehi);   // exact: kf*LN2N_HI has <= 52 bits
-  rr = pow_fma(kf, -LGAR_LN2N_LO, rr);
+  const double zz = ehi * PCK(PC_INVLN2N);
+  const double kf = (zz + PCK(PC_SHIFT)) - PCK(PC_SHIFT);  // rint(zz), |zz| < 2^17
+  const int ki = ok ? (int)kf : 0;
+  double rr = pow_fma(kf, PCK(PC_LN2N_HI), ehi);   // exact: kf*LN2N_HI has <= 52 bits
+  rr = pow_fma(kf, PCK(PC_LN2N_LO), rr);
   rr = rr + elo;
   const int j = (int)(ki & (LGAR_POW_N - 1));
 #ifdef __CUDA_ARCH__
@@ -136,12 +152,12 @@ LGAR_HD double pow_core(double x, double y, bool& ok) {
 #else
   const double tj = h_pow_exp_table[j].t, tailj = h_pow_exp_table[j].tail;
 #endif
-  const uint64_t sbits = pow_bits(tj) + ((uint64_t)(ki >> 7) << 52);
+  const uint64_t sbits = pow_bits(tj) + ((uint64_t)(int64_t)(ki >> 7) << 52);
   const double scale = pow_from_bits(sbits);
   const double rr2 = rr * rr;
-  double e2 = pow_fma(rr, LGAR_EXP_C3, LGAR_EXP_C2);
-  double e4 = pow_fma(rr, LGAR_EXP_C5, LGAR_EXP_C4);
-  e4 = pow_fma(rr2, LGAR_EXP_C6, e4);
+  double e2 = pow_fma(rr, PCK(PC_C3), PCK(PC_C2));
+  double e4 = pow_fma(rr, PCK(PC_C5), PCK(PC_C4));
+  e4 = pow_fma(rr2, PCK(PC_C6), e4);
   const double tmp2 = tailj + (rr + (rr2 * e2 + (rr2 * rr2) * e4));
   const double res = pow_fma(scale, tmp2, scale);
   // |y log x| tiny: pow = 1 + y log x to well below half an ulp
