@@ -1078,7 +1078,7 @@ struct Column {
             if (probe) {
               const bool cont = up ? (mass_layers > prior_mass) : (mass_layers <= prior_mass);
               const bool ok = cont && cc.st == 0 && dm > tol && (psi_try > 64.0 * step) &&
-                              fabs(mass_layers - new_mass) >= 1e-12 * (double)stride;
+                              fabs(mass_layers - new_mass) >= 1e-13 * (double)stride;  // 100x the stall guard
               if (ok) {  // identical to `stride` regular iterations of this run
                 psi_cm = psi_try;
                 psi_prev = psi_prev_try;
@@ -1148,7 +1148,7 @@ struct Column {
                 const double psi_star = psi_cm - (mass_layers - prior_mass) * (psi_cm - psi_a) / (mass_layers - mass_a);
                 const double kest = (psi_cm - psi_star) / s2;
                 // (skip when one fine step changes the mass by less than the probe's monotonicity margin)
-                if (kest >= 3.0 && kest <= 4096.0 && psi_cm > 128.0 * s2 && fabs(mass_layers - mass_a) >= 4e-11) {
+                if (kest >= 3.0 && kest <= 4096.0 && psi_cm > 128.0 * s2 && fabs(mass_layers - mass_a) >= 4e-12) {
                   stride = (long long)kest - 1;  // one step of margin before the estimated crossing
                   pred = true;
                   run_up = false;

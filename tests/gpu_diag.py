@@ -21,9 +21,12 @@ for B, T in shapes:
     torch.cuda.synchronize(); t0 = time.time()
     res, ws = forward_raw(ens, we.alpha, we.n, we.ksat, outputs=("runoff", "AET"), counters=True, tile_cycles=True)
     torch.cuda.synchronize(); dt = time.time() - t0
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record(); forward_raw(ens, we.alpha, we.n, we.ksat, outputs=("runoff", "AET"), workspace=ws); e1.record()
-    torch.cuda.synchronize(); kms = e0.elapsed_time(e1)
+    times = []
+    for _ in range(int(os.environ.get("LGAR_DIAG_REPS", "3"))):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); forward_raw(ens, we.alpha, we.n, we.ksat, outputs=("runoff", "AET"), workspace=ws); e1.record()
+        torch.cuda.synchronize(); times.append(e0.elapsed_time(e1))
+    kms = min(times)
     st = res.status.cpu().numpy(); cr = res.crash_step.cpu().numpy()
     alive = int(np.where(st == 0, T, np.maximum(cr, 0)).sum())
     if os.environ.get("LGAR_DIAG_SAVE"):
@@ -31,4 +34,4 @@ for B, T in shapes:
         np.savez_compressed(f"gpurun_out/diag_{B}x{T}.npz", sums=res.sums.cpu().numpy(), status=st, crash=cr)
     tc = res.tile_cycles.cpu().numpy(); top = np.argsort(-tc)[:4]
     print("  slowest tiles:", [(int(i), round(float(tc[i]) / 1.9e9, 2)) for i in top], "median tile s", round(float(np.median(tc)) / 1.9e9, 3), flush=True)
-    print(f"B={B} T={T}: first {dt:.3f}s, 2nd pass {kms:.1f} ms -> {alive/kms*1e3:.4g} col-steps/s  alive col-steps={alive}  status hist={np.bincount(st, minlength=9).tolist()} counters={res.counters.cpu().numpy().tolist()}", flush=True)
+    print(f"B={B} T={T}: first {dt:.3f}s, best of {len(times)} passes {kms:.1f} ms (all: {[round(x) for x in times]}) -> {alive/kms*1e3:.4g} col-steps/s  alive col-steps={alive}  status hist={np.bincount(st, minlength=9).tolist()} counters={res.counters.cpu().numpy().tolist()}", flush=True)
