@@ -81,6 +81,14 @@ int g_num_sms = 0;
 // the shared-memory footprint of the value + id arrays.
 #define LGAR_TAPE_CAP 6144  /* + leaves must stay below 32768: ids are stored as 16 bit in shared memory */
 int backward_ctas_per_sm(const Shape& s) { return s.FM == 16 ? 2 : (s.FM == 12 ? 2 : 4); }
+// tape arena of one chunk: average budget of LGAR_TAPE_AVG entries per sub-step (a sub-step may use up to
+// LGAR_TAPE_CAP); exhaustion flags the column (NaN gradient + tape_overflow)
+#define LGAR_TAPE_AVG 640
+int backward_arena_cap(const Shape& s) {
+  long long c = (long long)s.chunk * s.S * LGAR_TAPE_AVG;
+  if (c < LGAR_TAPE_CAP) c = LGAR_TAPE_CAP;
+  return (int)c;
+}
 int backward_slots(const Shape& s) {
   long long want = ((long long)s.ntiles + lgar::WARPS - 1) / lgar::WARPS;
   long long grid = 160LL * backward_ctas_per_sm(s);
@@ -161,18 +169,18 @@ int launch_backward(lgar::BParams& P, const Shape& s, unsigned char* scratch, cu
   if (grid > slots / lgar::WARPS) grid = slots / lgar::WARPS;
   if (grid < 1) grid = 1;
   const size_t ring_steps = (size_t)s.chunk * s.S;
-  const size_t nd = 5 * (size_t)FM + lgar::S_SUMS, nl = lgar::num_leaves<FM>();
+  const size_t nl = lgar::num_leaves<FM>();
+  const int arena_cap = backward_arena_cap(s);
   size_t o = 0;
   auto take = [&](size_t bytes) { unsigned char* q = scratch + o; o += (bytes + 255) / 256 * 256; return q; };
-  P.ring_d = (double*)take((size_t)slots * ring_steps * nd * 32 * 8);
-  P.ring_i = (int32_t*)take((size_t)slots * ring_steps * 2 * 32 * 4);
-  P.ring_f = (uint8_t*)take((size_t)slots * ring_steps * FM * 32);
-  P.tape = (lgar::TapeEntry*)take((size_t)slots * LGAR_TAPE_CAP * 32 * sizeof(lgar::TapeEntry));
+  P.tape = (lgar::TapeEntry*)take((size_t)slots * arena_cap * 32 * sizeof(lgar::TapeEntry));
+  P.meta = (unsigned char*)take((size_t)slots * ring_steps * 32 * sizeof(lgar::StepMeta<FM>));
   P.adj = (double*)take((size_t)slots * (nl + LGAR_TAPE_CAP) * 32 * 8);
   P.lam = (double*)take((size_t)slots * nl * 32 * 8);
   P.next_tile = (unsigned long long*)take(64);
   P.ring_steps = (int32_t)ring_steps;
-  P.tape_cap = LGAR_TAPE_CAP;
+  P.arena_cap = arena_cap;
+  P.step_cap = LGAR_TAPE_CAP;
   CUDA_TRY(cudaMemsetAsync(P.next_tile, 0, 64, st));
   kern<<<(unsigned)grid, lgar::NT, smem, st>>>(P);
   CUDA_TRY(cudaGetLastError());
@@ -206,7 +214,7 @@ size_t lgar_workspace_bytes(const lgar_problem* p, int with_grad) {
   size_t total = carve(s, with_grad).total;
 #ifdef LGAR_WITH_BACKWARD
   if (with_grad)
-    total += lgar::backward_scratch_bytes(s.B, s.Bp, s.L, s.S, s.FM, s.chunk, backward_slots(s), LGAR_TAPE_CAP);
+    total += lgar::backward_scratch_bytes(s.S, s.FM, s.chunk, backward_slots(s), backward_arena_cap(s), LGAR_TAPE_CAP);
 #endif
   return total;
 }
