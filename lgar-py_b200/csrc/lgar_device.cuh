@@ -427,20 +427,32 @@ struct SoilT<Var> : Soil {
 
 // ---- theta(h)
 __device__ __forceinline__ double thetaR(double h, const SoilT<double>& s, Ctx& c) { return theta_from_h(h, s, c); }
-__device__ __forceinline__ Var thetaR(const Var& h, const SoilT<Var>& s, Ctx& c) {
-  const double v = theta_from_h(h.v, s, c);
-  // x = alpha h; ap = x^n; u = 1 + ap; o = u^m; theta = (the - thr)/o + thr
-  const double x = s.alpha * h.v;
-  const double ap = pow_f64(x, s.n);
+struct P4 {
+  double a, b, c, d;
+};
+// partials of theta(h; alpha, n, m): x = alpha h; ap = x^n; u = 1 + ap; o = u^m; theta = (the - thr)/o + thr
+__device__ __noinline__ P4 theta_partials(double h, double alpha, double n, double m, double span) {
+  const double x = alpha * h;
+  const double ap = pow_f64(x, n);
   const double u = 1.0 + ap;
-  const double o = pow_f64(u, s.m);
-  const double dth_do = -(s.the - s.thr) / (o * o);
-  const double do_du = s.m * o / u;
-  const double dap_dx = (x == 0.0) ? 0.0 : s.n * ap / x;
+  const double o = pow_f64(u, m);
+  const double dth_do = -span / (o * o);
+  const double do_du = m * o / u;
+  const double dap_dx = (x == 0.0) ? 0.0 : n * ap / x;
   const double dap_dn = (x == 0.0) ? 0.0 : ap * log(x);
   const double g = dth_do * do_du;
+  P4 r;
+  r.a = g * dap_dx * alpha;  // d/dh
+  r.b = g * dap_dx * h;      // d/dalpha
+  r.c = g * dap_dn;          // d/dn
+  r.d = dth_do * o * log(u); // d/dm
+  return r;
+}
+__device__ __forceinline__ Var thetaR(const Var& h, const SoilT<Var>& s, Ctx& c) {
+  const double v = theta_from_h(h.v, s, c);
+  const P4 q = theta_partials(h.v, s.alpha, s.n, s.m, s.the - s.thr);
   const int ids[4] = {h.id, s.id_alpha, s.id_n, s.id_m};
-  const double d[4] = {g * dap_dx * s.alpha, g * dap_dx * h.v, g * dap_dn, dth_do * o * log(u)};
+  const double d[4] = {q.a, q.b, q.c, q.d};
   return tape_record_n(v, 4, ids, d);
 }
 // ---- Se(theta)
@@ -449,20 +461,30 @@ __device__ __forceinline__ Var se_thetaR(const Var& theta, const SoilT<Var>& s, 
   return tape_record(se_from_theta(theta.v, s, c), theta.id, 1.0 / (s.the - s.thr), -1, 0.0);
 }
 // ---- h(Se) partials: sp = se^(-1/m); base = sp - 1; op = base^(1/n); h = op / alpha
-__device__ __forceinline__ void h_se_partials(double se, const Soil& s, double hval, double* d_se, double* d_alpha,
-                                              double* d_n, double* d_m) {
-  const double sp = pow_f64(se, s.ninv_m);
+__device__ __noinline__ P4 h_se_partials_core(double se, double alpha, double ninv_m, double inv_m, double inv_n,
+                                              double hval) {
+  const double sp = pow_f64(se, ninv_m);
   double base = sp - 1.0;
   if (fabs(base) <= 1e-8) base = base + 1e-12;
-  const double op = hval * s.alpha;
-  const double dop_dbase = s.inv_n * op / base;
-  const double dsp_dse = (se == 0.0) ? 0.0 : s.ninv_m * sp / se;
-  const double dsp_dm = (se == 0.0) ? 0.0 : sp * log(se) * (s.inv_m * s.inv_m);  // d(-1/m)/dm = 1/m^2
-  const double dop_dn = (base == 0.0) ? 0.0 : op * log(base) * (-(s.inv_n * s.inv_n));
-  *d_se = dop_dbase * dsp_dse / s.alpha;
-  *d_alpha = -hval / s.alpha;
-  *d_n = dop_dn / s.alpha;
-  *d_m = dop_dbase * dsp_dm / s.alpha;
+  const double op = hval * alpha;
+  const double dop_dbase = inv_n * op / base;
+  const double dsp_dse = (se == 0.0) ? 0.0 : ninv_m * sp / se;
+  const double dsp_dm = (se == 0.0) ? 0.0 : sp * log(se) * (inv_m * inv_m);  // d(-1/m)/dm = 1/m^2
+  const double dop_dn = (base == 0.0) ? 0.0 : op * log(base) * (-(inv_n * inv_n));
+  P4 r;
+  r.a = dop_dbase * dsp_dse / alpha;  // d/dse
+  r.b = -hval / alpha;                // d/dalpha
+  r.c = dop_dn / alpha;               // d/dn
+  r.d = dop_dbase * dsp_dm / alpha;   // d/dm
+  return r;
+}
+__device__ __forceinline__ void h_se_partials(double se, const Soil& s, double hval, double* d_se, double* d_alpha,
+                                              double* d_n, double* d_m) {
+  const P4 r = h_se_partials_core(se, s.alpha, s.ninv_m, s.inv_m, s.inv_n, hval);
+  *d_se = r.a;
+  *d_alpha = r.b;
+  *d_n = r.c;
+  *d_m = r.d;
 }
 __device__ __forceinline__ double h_seR(double se, const SoilT<double>& s, Ctx& c) { return h_from_se(se, s, c); }
 __device__ __forceinline__ Var h_seR(const Var& se, const SoilT<Var>& s, Ctx& c) {
@@ -474,8 +496,15 @@ __device__ __forceinline__ Var h_seR(const Var& se, const SoilT<Var>& s, Ctx& c)
   return tape_record_n(v, 4, ids, d);
 }
 // ---- K(Se) partials: sp = se^(1/m); base = 1 - sp; op = base^m; t = 1 - op; K = ksat sqrt(se) t^2
+__device__ __noinline__ P4 k_se_partials_core(double se, double ksat, double m, double inv_m);
 __device__ __forceinline__ void k_se_partials(double se, double ksat, double m, double inv_m, double* d_se, double* d_ksat,
                                               double* d_m) {
+  const P4 r = k_se_partials_core(se, ksat, m, inv_m);
+  *d_se = r.a;
+  *d_ksat = r.b;
+  *d_m = r.c;
+}
+__device__ __noinline__ P4 k_se_partials_core(double se, double ksat, double m, double inv_m) {
   const double sp = pow_f64(se, inv_m);
   double base = 1.0 - sp;
   if (fabs(base) <= 1e-8) base = base + 1e-12;
@@ -487,9 +516,12 @@ __device__ __forceinline__ void k_se_partials(double se, double ksat, double m, 
   const double ndop_dse = op * sp_over / base;
   const double lnse = (se == 0.0) ? 0.0 : log(se);
   const double dop_dm = op * log(base) + op * sp * lnse / (base * m);
-  *d_se = ksat * ((rs == 0.0 ? 0.0 : t * t / (2.0 * rs)) + 2.0 * t * rs * ndop_dse);
-  *d_ksat = rs * (t * t);
-  *d_m = ksat * rs * 2.0 * t * (-dop_dm);
+  P4 r;
+  r.a = ksat * ((rs == 0.0 ? 0.0 : t * t / (2.0 * rs)) + 2.0 * t * rs * ndop_dse);  // d/dse
+  r.b = rs * (t * t);                                                                // d/dksat
+  r.c = ksat * rs * 2.0 * t * (-dop_dm);                                             // d/dm
+  r.d = 0.0;
+  return r;
 }
 __device__ __forceinline__ double k_seR(double se, const SoilT<double>& s, Ctx& c) {
   return k_from_se(se, s.ksat, s.m, s.inv_m, c);
