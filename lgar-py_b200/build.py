@@ -9,12 +9,12 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "liblgar_b200.so")
-SOURCES = ["lgar_capi.cu"]
-HEADERS = ["lgar_device.cuh", "lgar_forward.cuh", "lgar_backward.cuh", "lgar_pow.cuh", "lgar_pow_tables.h",
+SOURCES = ["lgar_capi.cu", "lgar_backward_launch.cu"]
+HEADERS = ["lgar_device.cuh", "lgar_forward.cuh", "lgar_backward.cuh", "lgar_pow.cuh", "lgar_pow_tables.h", "lgar_var.cuh",
            "../../include/lgar_b200.h"]
 
 NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--threads", "2",
     # no FMA contraction: every product and sum rounds separately, like the reference's torch ops
     "--fmad=false",
     "-Xcompiler", "-fPIC", "-shared",
@@ -40,7 +40,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         flags += ["-DLGAR_WITH_BACKWARD"]
     if verbose:
         flags += ["-Xptxas", "-v"]
-    cmd = ["nvcc", *flags, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
+    flags += os.environ.get("LGAR_EXTRA_NVCC_FLAGS", "").split()  # developer A/B switches
+    cmd = ["nvcc", *flags, "-o", os.environ.get("LGAR_BUILD_OUT", LIB), *[os.path.join(CSRC, s) for s in SOURCES]]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -1,0 +1,72 @@
+// =====================================================================================
+// lgar_backward_launch.cu -- the reverse-mode kernel's own translation unit.
+// Compiled separately from lgar_capi.cu (forward kernel) so that the two kernels can make different
+// shared-memory trade-offs: the reverse kernel needs every byte of its 2-CTAs-per-SM budget for the value +
+// tape-id arrays and therefore keeps the pow tables in global memory (L1), the forward kernel copies them
+// to shared memory.  Also halves the build time (the two units compile in parallel).
+// =====================================================================================
+#define LGAR_POW_TABLES_GLOBAL 1
+// every header symbol of this unit lives in its own namespace: the host-side stubs of the __device__ functions
+// would otherwise collide with the forward unit's at link time (and the two units compile them differently)
+#define lgar lgar_reverse_unit
+#include <cstdio>
+
+#include "lgar_backward.cuh"
+
+namespace lgar {
+
+#define BW_TRY(expr)                                                                      \
+  do {                                                                                    \
+    cudaError_t e__ = (expr);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      std::snprintf(err, errlen, "%s failed: %s", #expr, cudaGetErrorString(e__));        \
+      return LGAR_E_CUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+template <int FM>
+static int launch_backward(BParams& P, int S, int chunk, int slots, int arena_cap, int step_cap, int num_sms,
+                           unsigned char* scratch, cudaStream_t st, char* err, size_t errlen) {
+  auto kern = lgar_backward_kernel<FM>;
+  const size_t smem = (size_t)5 * FM * NT * sizeof(double) + (size_t)WARPS * NODEBUF * sizeof(double) +
+                      (size_t)5 * FM * NT * sizeof(short) + (size_t)FM * NT;
+  BW_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  BW_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+  if (per_sm < 1) {
+    std::snprintf(err, errlen, "backward kernel does not fit on an SM");
+    return LGAR_E_CUDA;
+  }
+  long long grid = (long long)num_sms * per_sm;
+  if (grid > slots / WARPS) grid = slots / WARPS;
+  if (grid < 1) grid = 1;
+  const size_t ring_steps = (size_t)chunk * S;
+  const size_t nl = num_leaves<FM>();
+  size_t o = 0;
+  auto take = [&](size_t bytes) { unsigned char* q = scratch + o; o += (bytes + 255) / 256 * 256; return q; };
+  P.tape = (TapeEntry*)take((size_t)slots * arena_cap * 32 * sizeof(TapeEntry));
+  P.meta = (unsigned char*)take((size_t)slots * ring_steps * 32 * sizeof(StepMeta<FM>));
+  P.adj = (double*)take((size_t)slots * (nl + step_cap) * 32 * 8);
+  P.lam = (double*)take((size_t)slots * nl * 32 * 8);
+  P.next_tile = (unsigned long long*)take(64);
+  P.ring_steps = (int32_t)ring_steps;
+  P.arena_cap = arena_cap;
+  P.step_cap = step_cap;
+  BW_TRY(cudaMemsetAsync(P.next_tile, 0, 64, st));
+  kern<<<(unsigned)grid, NT, smem, st>>>(P);
+  BW_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace lgar
+
+// opaque-pointer entry used by lgar_capi.cu (BParams has the same layout in both units: same header)
+int lgar_reverse_unit_launch(int FM, void* params, int S, int chunk, int slots, int arena_cap, int step_cap, int num_sms,
+                             unsigned char* scratch, void* stream, char* err, size_t errlen) {
+  using namespace lgar;
+  BParams& P = *static_cast<BParams*>(params);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (FM == 8) return launch_backward<8>(P, S, chunk, slots, arena_cap, step_cap, num_sms, scratch, st, err, errlen);
+  if (FM == 12) return launch_backward<12>(P, S, chunk, slots, arena_cap, step_cap, num_sms, scratch, st, err, errlen);
+  return launch_backward<16>(P, S, chunk, slots, arena_cap, step_cap, num_sms, scratch, st, err, errlen);
+}

@@ -154,39 +154,9 @@ struct DevBuf {
 
 
 #ifdef LGAR_WITH_BACKWARD
-namespace {
-template <int FM>
-int launch_backward(lgar::BParams& P, const Shape& s, unsigned char* scratch, cudaStream_t st) {
-  auto kern = lgar::lgar_backward_kernel<FM>;
-  const size_t smem = (size_t)5 * FM * lgar::NT * sizeof(double) + (size_t)lgar::WARPS * lgar::NODEBUF * sizeof(double) +
-                      (size_t)5 * FM * lgar::NT * sizeof(short) + (size_t)FM * lgar::NT;
-  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, lgar::NT, smem));
-  if (per_sm < 1) return fail(LGAR_E_CUDA, "backward kernel does not fit on an SM");
-  const int slots = backward_slots(s);
-  long long grid = (long long)g_num_sms * per_sm;
-  if (grid > slots / lgar::WARPS) grid = slots / lgar::WARPS;
-  if (grid < 1) grid = 1;
-  const size_t ring_steps = (size_t)s.chunk * s.S;
-  const size_t nl = lgar::num_leaves<FM>();
-  const int arena_cap = backward_arena_cap(s);
-  size_t o = 0;
-  auto take = [&](size_t bytes) { unsigned char* q = scratch + o; o += (bytes + 255) / 256 * 256; return q; };
-  P.tape = (lgar::TapeEntry*)take((size_t)slots * arena_cap * 32 * sizeof(lgar::TapeEntry));
-  P.meta = (unsigned char*)take((size_t)slots * ring_steps * 32 * sizeof(lgar::StepMeta<FM>));
-  P.adj = (double*)take((size_t)slots * (nl + LGAR_TAPE_CAP) * 32 * 8);
-  P.lam = (double*)take((size_t)slots * nl * 32 * 8);
-  P.next_tile = (unsigned long long*)take(64);
-  P.ring_steps = (int32_t)ring_steps;
-  P.arena_cap = arena_cap;
-  P.step_cap = LGAR_TAPE_CAP;
-  CUDA_TRY(cudaMemsetAsync(P.next_tile, 0, 64, st));
-  kern<<<(unsigned)grid, lgar::NT, smem, st>>>(P);
-  CUDA_TRY(cudaGetLastError());
-  return 0;
-}
-}  // namespace
+// the reverse kernel is compiled in its own translation unit (lgar_backward_launch.cu)
+int lgar_reverse_unit_launch(int FM, void* params, int S, int chunk, int slots, int arena_cap, int step_cap, int num_sms,
+                             unsigned char* scratch, void* stream, char* err, size_t errlen);
 #endif
 
 extern "C" {
@@ -313,9 +283,8 @@ int lgar_backward(const lgar_problem* p, const double* grad_per_step, uint32_t g
   P.grad_n = grad_n;
   P.grad_ksat = grad_ksat;
   unsigned char* scratch = w + c.total;
-  if (s.FM == 8) return launch_backward<8>(P, s, scratch, st);
-  if (s.FM == 12) return launch_backward<12>(P, s, scratch, st);
-  return launch_backward<16>(P, s, scratch, st);
+  return lgar_reverse_unit_launch(s.FM, &P, s.S, s.chunk, backward_slots(s), backward_arena_cap(s), LGAR_TAPE_CAP, g_num_sms,
+                                  scratch, (void*)st, g_err, sizeof(g_err));
 }
 #endif
 

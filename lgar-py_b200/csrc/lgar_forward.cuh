@@ -206,7 +206,7 @@ __device__ void substep(Tile<FM, R>& T, bool act, double precip_rate, double pet
   {
     const bool go = act && c.st == 0 && (brA || !create);
     const R infil_arg = create ? R(0.0) : infiltration_sub;
-    const R bottom = C.move_wetting_front_warp(go, fd, infil_arg, AET_sub, ending_volume_sub, dt, c);
+    const R bottom = C.move_wetting_front_warp(go, fd, infil_arg, AET_sub, ending_volume_sub, dt, c, nodebuf);
     if (go && !create) {
       percolation_sub = bottom;
       T.acc[LGAR_OUT_PERCOLATION] = T.acc[LGAR_OUT_PERCOLATION] + percolation_sub;
@@ -427,6 +427,7 @@ __global__ void __launch_bounds__(NT, (FM == 16) ? 2 : ((FM == 12) ? 3 : 4)) lga
   double* sm_nodes = sm_fields + 5 * FM * NT;                                    // [WARPS][NODEBUF]
   uint8_t* sm_flags = reinterpret_cast<uint8_t*>(sm_nodes + WARPS * NODEBUF);    // [FM][NT]
   __shared__ unsigned long long sm_item[WARPS];
+  pow_tables_to_shared();
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;

@@ -41,6 +41,29 @@ struct PowExpEntry { double t, tail; };
 #ifdef __CUDACC__
 __device__ const PowLogEntry g_pow_log_table[LGAR_POW_N] = {LGAR_POW_LOG_TABLE};
 __device__ const PowExpEntry g_pow_exp_table[LGAR_POW_N] = {LGAR_POW_EXP_TABLE};
+// Per-CTA copies in shared memory (6 KB): the look-ups are data-dependent, so a warp touches up to 32
+// different rows; from shared memory that is a few wavefronts at ~25 cycles instead of 32 L1 tag look-ups
+// at global-load latency on the critical path of every pow.  Every kernel that evaluates pow_core on the
+// device calls pow_tables_to_shared() once before its first pow.
+// (LGAR_POW_TABLES_GLOBAL: the translation unit keeps them in global memory / L1 instead -- the reverse kernel,
+// whose shared memory is fully booked by the value + tape-id arrays.)
+#ifndef LGAR_POW_TABLES_GLOBAL
+__shared__ double2 s_pow_log_table[2 * LGAR_POW_N];
+__shared__ double2 s_pow_exp_table[LGAR_POW_N];
+__device__ __forceinline__ void pow_tables_to_shared() {
+  for (int i = threadIdx.x; i < 2 * LGAR_POW_N; i += blockDim.x)
+    s_pow_log_table[i] = reinterpret_cast<const double2*>(g_pow_log_table)[i];
+  for (int i = threadIdx.x; i < LGAR_POW_N; i += blockDim.x)
+    s_pow_exp_table[i] = reinterpret_cast<const double2*>(g_pow_exp_table)[i];
+  __syncthreads();
+}
+#define LGAR_POW_LOG_ROW(i2) s_pow_log_table[i2]
+#define LGAR_POW_EXP_ROW(j) s_pow_exp_table[j]
+#else
+__device__ __forceinline__ void pow_tables_to_shared() {}
+#define LGAR_POW_LOG_ROW(i2) __ldg(reinterpret_cast<const double2*>(g_pow_log_table) + (i2))
+#define LGAR_POW_EXP_ROW(j) __ldg(reinterpret_cast<const double2*>(g_pow_exp_table) + (j))
+#endif
 #endif
 static const PowLogEntry h_pow_log_table[LGAR_POW_N] = {LGAR_POW_LOG_TABLE};
 static const PowExpEntry h_pow_exp_table[LGAR_POW_N] = {LGAR_POW_EXP_TABLE};
@@ -53,7 +76,7 @@ enum PowConst { PC_LN2HI, PC_LN2LO, PC_INVLN2N, PC_LN2N_HI, PC_LN2N_LO, PC_A3, P
                          LGAR_LOG_A5, LGAR_LOG_A6, LGAR_LOG_A7, LGAR_LOG_A8, LGAR_LOG_A9, LGAR_EXP_C2, LGAR_EXP_C3, \
                          LGAR_EXP_C4, LGAR_EXP_C5, LGAR_EXP_C6, 0x1.8p52}
 #ifdef __CUDACC__
-__constant__ double c_pow_consts[PC_COUNT] = LGAR_POW_CONSTS;
+static __constant__ double c_pow_consts[PC_COUNT] = LGAR_POW_CONSTS;
 #endif
 static const double h_pow_consts[PC_COUNT] = LGAR_POW_CONSTS;
 #ifdef __CUDA_ARCH__
@@ -84,84 +107,116 @@ LGAR_HD double pow_fma(double a, double b, double c) {
 #endif
 }
 
-// Branch-free core.  Returns the fast-path value and sets ok = false when the arguments are outside
-// the fast path (the caller then uses the library pow).  Being branch-free, two or more calls in one
-// basic block are interleaved by the scheduler (ILP): see pow_x2 in lgar_device.cuh.
-LGAR_HD double pow_core(double x, double y, bool& ok) {
-  const uint64_t ix = pow_bits(x);
-  // x must be a positive normal number
-  const bool x_ok = (ix - 0x0010000000000000ULL) < (0x7ff0000000000000ULL - 0x0010000000000000ULL);
-  // ---- log(x) = hi + lo
-  const uint64_t tmp = ix - LGAR_POW_OFF;
-  const int i = (int)((tmp >> 45) & (LGAR_POW_N - 1));
-  const int k = (int)((int64_t)tmp >> 52);
-  const double z = pow_from_bits(ix - (tmp & 0xfff0000000000000ULL));
-  const double kd = (double)k;
+// Branch-free core, written for N independent evaluations at once: every statement is applied to all N
+// arguments before the next one, so the N dependent chains are interleaved IN SOURCE ORDER.  (Calling a scalar
+// core N times in a row does not do it: ptxas keeps the chains back to back -- checked in the SASS -- and a warp
+// then waits out the full FP64 latency of one chain after the other.)  Per element the operations are exactly the
+// same IEEE operations in the same order, so pow_core_v<N> is bit-identical to N scalar calls.
+// Sets ok[k] = false when the arguments are outside the fast path (the caller then uses the library pow).
+template <int N>
+LGAR_HD void pow_core_v(const double (&x)[N], const double (&y)[N], double (&res)[N], bool (&ok)[N]) {
+  bool x_ok[N];
+  int ki_[N];
+  double z[N], kd[N], invc[N], logc[N], logctail[N];
 #ifdef __CUDA_ARCH__
-  const double2 le0 = __ldg(reinterpret_cast<const double2*>(g_pow_log_table) + 2 * i);
-  const double2 le1 = __ldg(reinterpret_cast<const double2*>(g_pow_log_table) + 2 * i + 1);
-  const double invc = le0.x, logc = le0.y, logctail = le1.x;
-#else
-  const double invc = h_pow_log_table[i].invc, logc = h_pow_log_table[i].logc, logctail = h_pow_log_table[i].logctail;
+#pragma unroll
 #endif
-  const double p = z * invc;
-  const double rl = pow_fma(z, invc, -p);  // exact: z*invc = p + rl
-  const double r = p - 1.0;                // exact (Sterbenz)
-  const double t1 = pow_fma(kd, PCK(PC_LN2HI), logc);  // exact: both are multiples of 2^-42 below 2^10
+  for (int e = 0; e < N; e++) {
+    const uint64_t ix = pow_bits(x[e]);
+    // x must be a positive normal number
+    x_ok[e] = (ix - 0x0010000000000000ULL) < (0x7ff0000000000000ULL - 0x0010000000000000ULL);
+    // ---- log(x) = hi + lo
+    const uint64_t tmp = ix - LGAR_POW_OFF;
+    const int i = (int)((tmp >> 45) & (LGAR_POW_N - 1));
+    const int k = (int)((int64_t)tmp >> 52);
+    z[e] = pow_from_bits(ix - (tmp & 0xfff0000000000000ULL));
+    kd[e] = (double)k;
+#ifdef __CUDA_ARCH__
+    const double2 le0 = LGAR_POW_LOG_ROW(2 * i);
+    const double2 le1 = LGAR_POW_LOG_ROW(2 * i + 1);
+    invc[e] = le0.x; logc[e] = le0.y; logctail[e] = le1.x;
+#else
+    invc[e] = h_pow_log_table[i].invc; logc[e] = h_pow_log_table[i].logc; logctail[e] = h_pow_log_table[i].logctail;
+#endif
+  }
+#define LGAR_V(stmt)                        \
+  _Pragma("unroll") for (int e = 0; e < N; e++) { stmt; }
+  double p[N], rl[N], r[N], t1[N], t2[N], lo2[N], lo1[N], ar[N], ar2[N], lo3[N], hi[N], lo4[N], r2[N], q[N];
+  LGAR_V(p[e] = z[e] * invc[e])
+  LGAR_V(rl[e] = pow_fma(z[e], invc[e], -p[e]))  // exact: z*invc = p + rl
+  LGAR_V(r[e] = p[e] - 1.0)                      // exact (Sterbenz)
+  LGAR_V(t1[e] = pow_fma(kd[e], PCK(PC_LN2HI), logc[e]))  // exact: both are multiples of 2^-42 below 2^10
   // Fast2Sum t1 + r: exact because t1 == 0 (interval 64, k = 0) or |t1| >= |log c_63| = 0.0059 > |r|
-  const double t2 = t1 + r;
-  const double lo2 = (t1 - t2) + r;
-  const double lo1 = pow_fma(kd, PCK(PC_LN2LO), logctail);
+  LGAR_V(t2[e] = t1[e] + r[e])
+  LGAR_V(lo2[e] = (t1[e] - t2[e]) + r[e])
+  LGAR_V(lo1[e] = pow_fma(kd[e], PCK(PC_LN2LO), logctail[e]))
   // -r^2/2 in two terms
-  const double ar = -0.5 * r;
-  const double ar2 = r * ar;
-  const double lo3 = pow_fma(ar, r, -ar2);
-  const double hi = t2 + ar2;
-  const double lo4 = (t2 - hi) + ar2;
-  const double r2 = r * r;
+  LGAR_V(ar[e] = -0.5 * r[e])
+  LGAR_V(ar2[e] = r[e] * ar[e])
+  LGAR_V(lo3[e] = pow_fma(ar[e], r[e], -ar2[e]))
+  LGAR_V(hi[e] = t2[e] + ar2[e])
+  LGAR_V(lo4[e] = (t2[e] - hi[e]) + ar2[e])
+  LGAR_V(r2[e] = r[e] * r[e])
   // log1p(r) - r + r^2/2 = r^3 (A3 + A4 r + ... + A9 r^6): |r| <= 0.0046, truncation < 2^-70 relative
-  double q = pow_fma(r, PCK(PC_A9), PCK(PC_A8));
-  q = pow_fma(r, q, PCK(PC_A7));
-  q = pow_fma(r, q, PCK(PC_A6));
-  q = pow_fma(r, q, PCK(PC_A5));
-  q = pow_fma(r, q, PCK(PC_A4));
-  q = pow_fma(r, q, PCK(PC_A3));
-  const double pl = (r2 * r) * q;
+  LGAR_V(q[e] = pow_fma(r[e], PCK(PC_A9), PCK(PC_A8)))
+  LGAR_V(q[e] = pow_fma(r[e], q[e], PCK(PC_A7)))
+  LGAR_V(q[e] = pow_fma(r[e], q[e], PCK(PC_A6)))
+  LGAR_V(q[e] = pow_fma(r[e], q[e], PCK(PC_A5)))
+  LGAR_V(q[e] = pow_fma(r[e], q[e], PCK(PC_A4)))
+  LGAR_V(q[e] = pow_fma(r[e], q[e], PCK(PC_A3)))
+  double pl[N], lo5[N], lo[N], lhi[N], llo[N], ehi[N], elo[N], aeh[N];
+  LGAR_V(pl[e] = (r2[e] * r[e]) * q[e])
   // contribution of the product rounding error rl: rl * d/dr log1p(r) = rl (1 - r + r^2)
-  const double lo5 = pow_fma(rl, r2 - r, rl);
-  const double lo = ((lo1 + lo2) + (lo3 + lo4)) + (pl + lo5);
-  const double lhi = hi + lo;
-  const double llo = (hi - lhi) + lo;
+  LGAR_V(lo5[e] = pow_fma(rl[e], r2[e] - r[e], rl[e]))
+  LGAR_V(lo[e] = ((lo1[e] + lo2[e]) + (lo3[e] + lo4[e])) + (pl[e] + lo5[e]))
+  LGAR_V(lhi[e] = hi[e] + lo[e])
+  LGAR_V(llo[e] = (hi[e] - lhi[e]) + lo[e])
   // ---- ehi + elo = y * log(x)
-  const double ehi = y * lhi;
-  const double elo = pow_fma(y, llo, pow_fma(y, lhi, -ehi));
+  LGAR_V(ehi[e] = y[e] * lhi[e])
+  LGAR_V(elo[e] = pow_fma(y[e], llo[e], pow_fma(y[e], lhi[e], -ehi[e])))
   // result must stay well inside the normal range (also rejects NaN / inf in y)
-  const double aeh = ehi < 0.0 ? -ehi : ehi;
-  ok = x_ok && (aeh < 700.0);
+  LGAR_V(aeh[e] = ehi[e] < 0.0 ? -ehi[e] : ehi[e])
+  LGAR_V(ok[e] = x_ok[e] && (aeh[e] < 700.0))
   // ---- exp(ehi + elo)
-  const double zz = ehi * PCK(PC_INVLN2N);
-  const double kf = (zz + PCK(PC_SHIFT)) - PCK(PC_SHIFT);  // rint(zz), |zz| < 2^17
-  const int ki = ok ? (int)kf : 0;
-  double rr = pow_fma(kf, PCK(PC_LN2N_HI), ehi);   // exact: kf*LN2N_HI has <= 52 bits
-  rr = pow_fma(kf, PCK(PC_LN2N_LO), rr);
-  rr = rr + elo;
-  const int j = (int)(ki & (LGAR_POW_N - 1));
+  double zz[N], kf[N], rr[N], tj[N], tailj[N], scale[N], rr2[N], e2[N], e4[N], tmp2[N];
+  LGAR_V(zz[e] = ehi[e] * PCK(PC_INVLN2N))
+  LGAR_V(kf[e] = (zz[e] + PCK(PC_SHIFT)) - PCK(PC_SHIFT))  // rint(zz), |zz| < 2^17
+  LGAR_V(ki_[e] = ok[e] ? (int)kf[e] : 0)
+  LGAR_V(rr[e] = pow_fma(kf[e], PCK(PC_LN2N_HI), ehi[e]))  // exact: kf*LN2N_HI has <= 52 bits
+  LGAR_V(rr[e] = pow_fma(kf[e], PCK(PC_LN2N_LO), rr[e]))
+  LGAR_V(rr[e] = rr[e] + elo[e])
 #ifdef __CUDA_ARCH__
-  const double2 ee = __ldg(reinterpret_cast<const double2*>(g_pow_exp_table) + j);
-  const double tj = ee.x, tailj = ee.y;
-#else
-  const double tj = h_pow_exp_table[j].t, tailj = h_pow_exp_table[j].tail;
+#pragma unroll
 #endif
-  const uint64_t sbits = pow_bits(tj) + ((uint64_t)(int64_t)(ki >> 7) << 52);
-  const double scale = pow_from_bits(sbits);
-  const double rr2 = rr * rr;
-  double e2 = pow_fma(rr, PCK(PC_C3), PCK(PC_C2));
-  double e4 = pow_fma(rr, PCK(PC_C5), PCK(PC_C4));
-  e4 = pow_fma(rr2, PCK(PC_C6), e4);
-  const double tmp2 = tailj + (rr + (rr2 * e2 + (rr2 * rr2) * e4));
-  const double res = pow_fma(scale, tmp2, scale);
+  for (int e = 0; e < N; e++) {
+    const int j = (int)(ki_[e] & (LGAR_POW_N - 1));
+#ifdef __CUDA_ARCH__
+    const double2 ee = LGAR_POW_EXP_ROW(j);
+    tj[e] = ee.x; tailj[e] = ee.y;
+#else
+    tj[e] = h_pow_exp_table[j].t; tailj[e] = h_pow_exp_table[j].tail;
+#endif
+    const uint64_t sbits = pow_bits(tj[e]) + ((uint64_t)(int64_t)(ki_[e] >> 7) << 52);
+    scale[e] = pow_from_bits(sbits);
+  }
+  LGAR_V(rr2[e] = rr[e] * rr[e])
+  LGAR_V(e2[e] = pow_fma(rr[e], PCK(PC_C3), PCK(PC_C2)))
+  LGAR_V(e4[e] = pow_fma(rr[e], PCK(PC_C5), PCK(PC_C4)))
+  LGAR_V(e4[e] = pow_fma(rr2[e], PCK(PC_C6), e4[e]))
+  LGAR_V(tmp2[e] = tailj[e] + (rr[e] + (rr2[e] * e2[e] + (rr2[e] * rr2[e]) * e4[e])))
   // |y log x| tiny: pow = 1 + y log x to well below half an ulp
-  return (aeh < 0x1p-60) ? (1.0 + ehi) : res;
+  LGAR_V(res[e] = (aeh[e] < 0x1p-60) ? (1.0 + ehi[e]) : pow_fma(scale[e], tmp2[e], scale[e]))
+#undef LGAR_V
+}
+
+// scalar form (the CPU accuracy harness and the single-evaluation closures)
+LGAR_HD double pow_core(double x, double y, bool& ok) {
+  const double xv[1] = {x}, yv[1] = {y};
+  double rv[1];
+  bool okv[1];
+  pow_core_v<1>(xv, yv, rv, okv);
+  ok = okv[0];
+  return rv[0];
 }
 
 // returns true and sets *out on the fast path; false -> caller must use the library pow

@@ -31,7 +31,7 @@ for B, T in shapes:
     alive = int(np.where(st == 0, T, np.maximum(cr, 0)).sum())
     if os.environ.get("LGAR_DIAG_SAVE"):
         os.makedirs("gpurun_out", exist_ok=True)
-        np.savez_compressed(f"gpurun_out/diag_{B}x{T}.npz", sums=res.sums.cpu().numpy(), status=st, crash=cr)
+        np.savez_compressed(f"gpurun_out/diag_{B}x{T}{os.environ.get('LGAR_DIAG_TAG', '')}.npz", sums=res.sums.cpu().numpy(), status=st, crash=cr)
     tc = res.tile_cycles.cpu().numpy(); top = np.argsort(-tc)[:4]
     print("  slowest tiles:", [(int(i), round(float(tc[i]) / 1.9e9, 2)) for i in top], "median tile s", round(float(np.median(tc)) / 1.9e9, 3), flush=True)
     print(f"B={B} T={T}: first {dt:.3f}s, best of {len(times)} passes {kms:.1f} ms (all: {[round(x) for x in times]}) -> {alive/kms*1e3:.4g} col-steps/s  alive col-steps={alive}  status hist={np.bincount(st, minlength=9).tolist()} counters={res.counters.cpu().numpy().tolist()}", flush=True)
