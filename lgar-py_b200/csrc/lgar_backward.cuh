@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(NT) lgar_backward_kernel(const BParams P) {
   short* sm_ids = reinterpret_cast<short*>(sm_nodes + WARPS * NODEBUF);          // [5*FM][NT]
   uint8_t* sm_flags = reinterpret_cast<uint8_t*>(sm_ids + 5 * FM * NT);          // [FM][NT]
   __shared__ unsigned long long sm_item[WARPS];
+  pow_tables_to_shared();
 
   const KParams& K = P.K;
   const lgar_problem& p = K.p;

@@ -45,25 +45,25 @@ __device__ const PowExpEntry g_pow_exp_table[LGAR_POW_N] = {LGAR_POW_EXP_TABLE};
 // different rows; from shared memory that is a few wavefronts at ~25 cycles instead of 32 L1 tag look-ups
 // at global-load latency on the critical path of every pow.  Every kernel that evaluates pow_core on the
 // device calls pow_tables_to_shared() once before its first pow.
-// (LGAR_POW_TABLES_GLOBAL: the translation unit keeps them in global memory / L1 instead -- the reverse kernel,
-// whose shared memory is fully booked by the value + tape-id arrays.)
+// LGAR_POW_TABLES_GLOBAL (the reverse kernel's unit, whose shared memory is booked by the value + tape-id
+// arrays): only the 2 KB exp table is copied, the 4 KB log table stays in global memory (L1).
 #ifndef LGAR_POW_TABLES_GLOBAL
 __shared__ double2 s_pow_log_table[2 * LGAR_POW_N];
+#define LGAR_POW_LOG_ROW(i2) s_pow_log_table[i2]
+#else
+#define LGAR_POW_LOG_ROW(i2) __ldg(reinterpret_cast<const double2*>(g_pow_log_table) + (i2))
+#endif
 __shared__ double2 s_pow_exp_table[LGAR_POW_N];
+#define LGAR_POW_EXP_ROW(j) s_pow_exp_table[j]
 __device__ __forceinline__ void pow_tables_to_shared() {
+#ifndef LGAR_POW_TABLES_GLOBAL
   for (int i = threadIdx.x; i < 2 * LGAR_POW_N; i += blockDim.x)
     s_pow_log_table[i] = reinterpret_cast<const double2*>(g_pow_log_table)[i];
+#endif
   for (int i = threadIdx.x; i < LGAR_POW_N; i += blockDim.x)
     s_pow_exp_table[i] = reinterpret_cast<const double2*>(g_pow_exp_table)[i];
   __syncthreads();
 }
-#define LGAR_POW_LOG_ROW(i2) s_pow_log_table[i2]
-#define LGAR_POW_EXP_ROW(j) s_pow_exp_table[j]
-#else
-__device__ __forceinline__ void pow_tables_to_shared() {}
-#define LGAR_POW_LOG_ROW(i2) __ldg(reinterpret_cast<const double2*>(g_pow_log_table) + (i2))
-#define LGAR_POW_EXP_ROW(j) __ldg(reinterpret_cast<const double2*>(g_pow_exp_table) + (j))
-#endif
 #endif
 static const PowLogEntry h_pow_log_table[LGAR_POW_N] = {LGAR_POW_LOG_TABLE};
 static const PowExpEntry h_pow_exp_table[LGAR_POW_N] = {LGAR_POW_EXP_TABLE};

@@ -102,8 +102,14 @@ class dpLGAR(nn.Module):
     def _ensemble(self, forcing, resume=False):
         L, B = len(self.alpha), self.columns
         rep = lambda v: np.repeat(np.asarray(v, dtype=np.float64).reshape(L, 1), B, axis=1)
+        f = torch.as_tensor(forcing, dtype=torch.float64)
+        site_index = None
+        if f.dim() == 3 and f.shape[0] > 1:  # one forcing record per column (sites of a calibration batch)
+            if f.shape[0] != B:
+                raise ValueError(f"forcing has {f.shape[0]} sites but the module holds {B} columns")
+            site_index = np.arange(B, dtype=np.int32)
         return ColumnEnsemble(theta_r=rep(self.theta_r), theta_e=rep(self.theta_e), thickness=rep(self.thickness),
-                              forcing=forcing, resume=resume, device=self.device, **self._ens_kw)
+                              forcing=f, site_index=site_index, resume=resume, device=self.device, **self._ens_kw)
 
     def _zero(self):
         return torch.tensor(0.0, dtype=torch.float64)

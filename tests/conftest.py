@@ -19,6 +19,8 @@ def golden_names(prefix=None, exclude_prefix=()):
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
     if prefix is not None:
         names = [n for n in names if n.startswith(prefix)]
+    if prefix is None:  # agent_* records hold one training epoch of the reference agent, not a column run
+        exclude_prefix = tuple(exclude_prefix) + ("agent_",)
     return [n for n in names if not any(n.startswith(e) for e in exclude_prefix)]
 
 

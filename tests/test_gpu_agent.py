@@ -1,0 +1,62 @@
+"""-m gpu: one training epoch of the calibration agent (lgar_b200.agent.DifferentiableLGAR) against one epoch of the
+UNMODIFIED reference agent (tests/golden/agent_phil_4550_200.npz, made by tests/golden/make_agent_golden.py):
+same observations, same per-step runoff, same loss, same parameter gradients and the same Adam update."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, max_excess
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(g, epochs=1):
+    return dict(
+        device="cuda", conversions=dict(hr_to_sec=3600.0, mm_to_cm=0.1),
+        constants=dict(frozen_factor=float(g["frozen_factor"]), nint=int(g["nint"])),
+        data=dict(layer_soil_type=[12, 13, 14], layer_thickness=[float(x) for x in g["layer_thickness"]],
+                  initial_psi=float(g["initial_psi"]), ponded_depth_max=float(g["ponded_depth_max"]),
+                  wilting_point_psi=float(g["wilting_point_psi"]), giuh_ordinates=[float(x) for x in g["giuh_ordinates"]]),
+        models=dict(endtime=float(g["nsteps"]), subcycle_length=3600.0, forcing_resolution=3600.0,
+                    hyperparameters=dict(warmup=int(g["warmup"]), epochs=epochs, learning_rate=float(g["lr"]),
+                                         lb=[float(v) for v in g["lb"]], ub=[float(v) for v in g["ub"]])))
+
+
+def test_one_epoch_equals_reference_agent():
+    from lgar_b200 import dpLGAR
+    from lgar_b200.agent import DifferentiableLGAR
+    g = load_golden("agent_phil_4550_200")
+    cfg = _cfg(g)
+    from lgar_b200.agent import derive_time_config
+    derive_time_config(cfg)
+    model = dpLGAR(cfg, theta_r=g["theta_r"], theta_e=g["theta_e"])
+    ag = DifferentiableLGAR(cfg, model=model, x=g["forcing"])
+    np.testing.assert_array_equal(ag.y[0].numpy(), g["y"])  # the reference's seeded "observations"
+    before = np.array([[float(p) for p in pl] for pl in (model.alpha, model.n, model.ksat)])
+    np.testing.assert_allclose(before, g["params_before"], rtol=0, atol=0)
+    ag.train_one_epoch()
+    assert max_excess(ag.y_hat[0].detach().cpu().numpy(), g["y_hat"]) <= 1.0
+    assert ag.history[0][1] == pytest.approx(float(g["loss_mse"]), rel=1e-9)   # bound loss is 0 inside the bounds
+    assert ag.history[0][2] == pytest.approx(float(g["nse"]), rel=1e-9)
+    assert abs(ag.last_balance_error) < 1e-8
+    grads = np.array([[float(p.grad) for p in pl] for pl in (model.alpha, model.n, model.ksat)])
+    ref = g["grads"]
+    np.testing.assert_allclose(grads, ref, rtol=1e-9, atol=1e-11 * np.abs(ref).max())
+    after = np.array([[float(p) for p in pl] for pl in (model.alpha, model.n, model.ksat)])
+    # Adam's first step is lr * g / (|g| + eps): entries with |g| ~ 1e-16 move by ~1e-11 and inherit g's noise
+    np.testing.assert_allclose(after, g["params_after"], rtol=1e-9, atol=1e-12)
+
+
+def test_two_sites_share_parameters():
+    """Two sites (the same record twice) in one launch: the averaged gradient equals the single-site gradient."""
+    from lgar_b200 import dpLGAR
+    from lgar_b200.agent import DifferentiableLGAR, derive_time_config
+    g = load_golden("agent_phil_4550_200")
+    cfg = derive_time_config(_cfg(g))
+    model = dpLGAR(cfg, theta_r=g["theta_r"], theta_e=g["theta_e"], columns=2)
+    x = np.stack([g["forcing"], g["forcing"]])
+    ag = DifferentiableLGAR(cfg, model=model, x=x, y=np.stack([g["y"], g["y"]]))
+    ag.train_one_epoch()
+    grads = np.array([[float(p.grad) for p in pl] for pl in (model.alpha, model.n, model.ksat)])
+    ref = g["grads"]
+    np.testing.assert_allclose(grads, ref, rtol=1e-9, atol=1e-11 * np.abs(ref).max())
