@@ -43,8 +43,14 @@ def test_one_epoch_equals_reference_agent():
     ref = g["grads"]
     np.testing.assert_allclose(grads, ref, rtol=1e-9, atol=1e-11 * np.abs(ref).max())
     after = np.array([[float(p) for p in pl] for pl in (model.alpha, model.n, model.ksat)])
-    # Adam's first step is lr * g / (|g| + eps): entries with |g| ~ 1e-16 move by ~1e-11 and inherit g's noise
-    np.testing.assert_allclose(after, g["params_after"], rtol=1e-9, atol=1e-12)
+    # Adam's first step is -lr * g / (|g| + eps): it turns a gradient of 1e-16 (round-off of the autograd graph, below
+    # the gradient tolerance) into a move of 1e-11, so the golden update is compared where the gradient is significant
+    # and the optimiser wiring is checked on our own gradients everywhere
+    lr, eps = float(g["lr"]), 1e-8
+    np.testing.assert_allclose(after - before, -lr * grads / (np.abs(grads) + eps), rtol=1e-6, atol=1e-15)  # after - before cancels to ~1 ulp of the parameter
+    big = np.abs(ref) > 1e-6 * np.abs(ref).max()
+    assert big.sum() >= 3
+    np.testing.assert_allclose(after[big], g["params_after"][big], rtol=1e-9, atol=0)
 
 
 def test_two_sites_share_parameters():
