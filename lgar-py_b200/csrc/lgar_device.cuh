@@ -77,6 +77,15 @@ __device__ __noinline__ double pow_f64(double a, double b) {
   const double r = pow_core(a, b, ok);  // lgar_pow.cuh: ~0.50 ulp
   return ok ? r : pow_slow(a, b);
 }
+// a^b together with log(a) (by-product of the pow core): derivative weights of the reverse kernel
+__device__ __noinline__ double2 pow_log_f64(double a, double b) {
+  const double xv[1] = {a}, yv[1] = {b};
+  double r[1], lg[1];
+  bool ok[1];
+  pow_core_v<1>(xv, yv, r, ok, lg);
+  if (!ok[0]) return make_double2(pow_slow(a, b), log(a));
+  return make_double2(r[0], lg[0]);
+}
 // two INDEPENDENT pows issued interleaved from one basic block (ILP: pow is one long dependent chain)
 __device__ __noinline__ double2 pow_x2(double x0, double y0, double x1, double y1) {
   const double xv[2] = {x0, x1}, yv[2] = {y0, y1};
@@ -660,22 +669,97 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
   return v;
 }
+// One trapezoid node with everything the reverse kernel needs, from ONE evaluation of the four pows: K (the same
+// operations as k_nodes_core_x2, hence the same bits as the forward kernel's node) and the partials of
+// K(Se(h; alpha, n, m); ksat, m); the logs come out of the pow cores.  node0: K_0 = K(Se_i) is a direct function of
+// Se_i in the reference graph (green_ampt.py:75), so Se is overridden by se0 after the guards of the first half
+// and the partial w.r.t. Se is reported instead of the h / alpha / n ones.
+struct NodeFull {
+  double K, dk_se, dk_h, dk_a, dk_n, dk_m;
+  int bad;
+};
+__device__ __noinline__ NodeFull k_node_full(double h, bool node0, double se0, double alpha, double n, double m,
+                                             double inv_m, double ksat) {
+  NodeFull r;
+  const bool w = fabs(h) < 1.0e-01;
+  const double x = w ? 1.0 : alpha * h;
+  int b = isnan(x) ? LGAR_ST_NAN : (x < 0.0 ? LGAR_ST_NEG_POW : 0);
+  const double2 pa = pow_log_f64(x, n);  // ap, log x
+  const double u = 1.0 + pa.x;
+  const double2 pu = pow_log_f64(u, m);  // u^m, log u
+  double se = 1.0 / pu.x;
+  if (!b && isnan(se)) b = LGAR_ST_NAN;
+  double dse_dh = 0.0, dse_da = 0.0, dse_dn = 0.0, dse_dm = 0.0;
+  if (w) {
+    se = 1.0;
+  } else {
+    const double dse_du = -m * se / u;
+    const double dap_dx = (x == 0.0) ? 0.0 : n * pa.x / x;
+    dse_dh = dse_du * dap_dx * alpha;
+    dse_da = dse_du * dap_dx * h;
+    dse_dn = (x == 0.0) ? 0.0 : dse_du * pa.x * pa.y;
+    dse_dm = -se * pu.y;
+  }
+  if (node0) {
+    se = se0;
+    dse_dh = dse_da = dse_dn = dse_dm = 0.0;
+  }
+  const double2 ps = pow_log_f64(se, inv_m);  // sp, log se
+  double base = 1.0 - ps.x;
+  if (fabs(base) <= 1e-8) base = base + 1e-12;
+  if (!b) b = isnan(base) ? LGAR_ST_NAN : (base < 0.0 ? LGAR_ST_NEG_POW : 0);
+  const double2 po = pow_log_f64(base, m);  // op, log base
+  const double t = 1.0 - po.x;
+  if (!b) b = isnan(t) ? LGAR_ST_NAN : (t < 0.0 ? LGAR_ST_NEG_POW : 0);
+  const double rs = sqrt(se);
+  r.K = ksat * rs * (t * t);
+  if (!b && isnan(r.K)) b = LGAR_ST_NAN;
+  r.bad = b;
+  // -dop/dse = op sp / (base se);  dop/dm = op ln(base) + op sp ln(se) / (base m)   (k_se_partials_core)
+  const double sp_over = (se == 0.0) ? 0.0 : ps.x / se;
+  const double ndop_dse = po.x * sp_over / base;
+  const double lnse = (se == 0.0) ? 0.0 : ps.y;
+  const double dop_dm = po.x * po.y + po.x * ps.x * lnse / (base * m);
+  const double dk_se = ksat * ((rs == 0.0 ? 0.0 : t * t / (2.0 * rs)) + 2.0 * t * rs * ndop_dse);
+  const double dk_m = ksat * rs * 2.0 * t * (-dop_dm);
+  r.dk_se = dk_se;
+  r.dk_h = dk_se * dse_dh;
+  r.dk_a = dk_se * dse_da;
+  r.dk_n = dk_se * dse_dn;
+  r.dk_m = dk_se * dse_dm + dk_m;
+  return r;
+}
+
+// Fused value + gradient pass of the reverse kernel: the node loop of geff_warp_core with k_node_full, i.e. four
+// pows per node for the value AND the partials (a separate partial pass cost four more pows and four logs).
 __device__ Var geff_warpR(bool need, const Var& theta_1, const Var& theta_2, const SoilT<Var>& s, int nint,
                           double* nodebuf, Ctx& c) {
-  const double value = geff_warp(need, theta_1.v, theta_2.v, s, nint, nodebuf, c);
   const int lane = threadIdx.x & 31;
-  // request scalars (same expressions as stage A of geff_warp)
-  double se_i = 1.0, se_f = 1.0, h_i = 0.0, h_f = 0.0;
-  Ctx cz = c;  // guards were already evaluated by the value pass
+  // stage A: the scalars of geff_warp_core, plus the end-point partials of h(Se) for every requesting lane at once
+  Ctx ca;
+  ca.st = 0;
+  double se_i = 1.0, se_f = 1.0, h_i = 0.0, h_f = 0.0, dh = 0.0, k0 = 0.0;
+  P4 pi, pf;
+  pi.a = pi.b = pi.c = pi.d = pf.a = pf.b = pf.c = pf.d = 0.0;
   if (need) {
-    se_i = se_from_theta(theta_1.v, s, cz);
-    se_f = se_from_theta(theta_2.v, s, cz);
-    const double2 hh = h_from_se_x2(se_i, se_f, s, cz);
+    se_i = se_from_theta(theta_1.v, s, ca);
+    se_f = se_from_theta(theta_2.v, s, ca);
+    const double2 hh = h_from_se_x2(se_i, se_f, s, ca);
     h_i = hh.x;
     h_f = hh.y;
+    if (fabs(h_i) >= 0.1 && s.alpha * h_i < 0.0) raise(ca, LGAR_ST_NEG_POW);  // "Checkpoint" calls, green_ampt.py:61-63
+    if (fabs(h_f) >= 0.1 && s.alpha * h_f < 0.0) raise(ca, LGAR_ST_NEG_POW);
+    dh = (h_f - h_i) / (double)nint;
+    k0 = k_from_se(se_i, s.ksat, s.m, s.inv_m, ca);
+    pi = h_se_partials_core(se_i, s.alpha, s.ninv_m, s.inv_m, s.inv_n, h_i);
+    pf = h_se_partials_core(se_f, s.alpha, s.ninv_m, s.inv_m, s.inv_n, h_f);
+    c.cnt[C_GEFF]++;
+    c.cnt[C_H_SE] += 2;
+    c.cnt[C_K_SE] += 1 + nint;
+    c.cnt[C_SE_H] += nint;
   }
   unsigned mask = __ballot_sync(0xffffffffu, need);
-  Var result(value);
+  Var result(0.0);
   while (mask) {
     const int src = __ffs(mask) - 1;
     mask &= mask - 1;
@@ -685,65 +769,71 @@ __device__ Var geff_warpR(bool need, const Var& theta_1, const Var& theta_2, con
     q.m = shfl_d(s.m, src);
     q.inv_m = shfl_d(s.inv_m, src);
     q.ksat = shfl_d(s.ksat, src);
-    const double qhi = shfl_d(h_i, src), qhf = shfl_d(h_f, src), qsei = shfl_d(se_i, src);
-    const double qdh = (qhf - qhi) / (double)nint;
+    const double qh = shfl_d(h_i, src), qdh = shfl_d(dh, src), qk0 = shfl_d(k0, src), qsei = shfl_d(se_i, src);
+    int cc_st = 0;
     double S = 0.0, Ahi = 0.0, Ahf = 0.0, Ca = 0.0, Cn = 0.0, Cm = 0.0, Csei = 0.0;
-    for (int k = lane; k <= nint; k += 32) {
-      const double w = (k == 0 || k == nint) ? 0.5 : 1.0;
-      double se, dse_dh = 0.0, dse_da = 0.0, dse_dn = 0.0, dse_dm = 0.0;
-      if (k == 0) {
-        se = qsei;
-      } else {
-        const double h = qhi + (double)k * qdh;  // derivative weights only: no need for the rounded chain
-        if (fabs(h) < 0.1) {
-          se = 1.0;
-        } else {
-          const double x = q.alpha * h;
-          const double ap = pow_f64(x, q.n);
-          const double u = 1.0 + ap;
-          se = 1.0 / pow_f64(u, q.m);
-          const double dse_du = -q.m * se / u;
-          const double dap_dx = (x == 0.0) ? 0.0 : q.n * ap / x;
-          dse_dh = dse_du * dap_dx * q.alpha;
-          dse_da = dse_du * dap_dx * h;
-          dse_dn = (x == 0.0) ? 0.0 : dse_du * ap * log(x);
-          dse_dm = -se * log(u);
+    double h = qh;
+    int done = 0;
+    for (int rdx = 0; rdx < 4; rdx++) {
+      const int target = lane + 32 * rdx;
+      if (target <= nint) {
+        if (target > done) {  // node abscissa: the rounded chain of the value pass (advance_rounded)
+          const double h0 = h;
+          h = advance_rounded(h0, qdh, target - done);
+          if (!(h > 0.0)) {
+            h = h0;
+            for (int w = done; w < target; w++) h = h + qdh;
+          }
+          done = target;
         }
+        const NodeFull nf = k_node_full(h, target == 0, qsei, q.alpha, q.n, q.m, q.inv_m, q.ksat);
+        if (nf.bad && cc_st == 0) cc_st = nf.bad;
+        const double kk = (target == 0) ? qk0 : nf.K;
+        nodebuf[target] = kk;
+        const double w = (target == 0 || target == nint) ? 0.5 : 1.0;
+        const double frac = (double)target / (double)nint;
+        S += w * kk;
+        if (target == 0) Csei += w * nf.dk_se;
+        Ahi += w * nf.dk_h * (1.0 - frac);
+        Ahf += w * nf.dk_h * frac;
+        Ca += w * nf.dk_a;
+        Cn += w * nf.dk_n;
+        Cm += w * nf.dk_m;
       }
-      double dk_se, dk_ks, dk_m;
-      k_se_partials(se, q.ksat, q.m, q.inv_m, &dk_se, &dk_ks, &dk_m);
-      const double kk = dk_ks * q.ksat;  // K itself
-      S += w * kk;
-      const double frac = (double)k / (double)nint;
-      if (k == 0) {
-        Csei += w * dk_se;
-      } else {
-        Ahi += w * dk_se * dse_dh * (1.0 - frac);
-        Ahf += w * dk_se * dse_dh * frac;
-        Ca += w * dk_se * dse_da;
-        Cn += w * dk_se * dse_dn;
-      }
-      Cm += w * (dk_se * dse_dm + dk_m);
     }
+    const unsigned badmask = __ballot_sync(0xffffffffu, cc_st != 0);
+    int st_any = 0;
+    if (badmask) st_any = __shfl_sync(0xffffffffu, cc_st, __ffs(badmask) - 1);
     S = warp_sum(S); Ahi = warp_sum(Ahi); Ahf = warp_sum(Ahf); Ca = warp_sum(Ca); Cn = warp_sum(Cn);
     Cm = warp_sum(Cm); Csei = warp_sum(Csei);
+    __syncwarp();
     if (lane == src) {
+      if (st_any) raise(ca, st_any);
+      const double half = qdh / 2.0;
+      double geff = 0.0;
+      double k1 = nodebuf[0];
+#pragma unroll 8
+      for (int i = 1; i <= nint; i++) {
+        const double k2 = nodebuf[i];
+        geff = geff + ((k1 + k2) * half);
+        k1 = k2;
+      }
+      const double value = fabs(geff / s.ksat);
       const double G = qdh * S;
       const double sg = (G / q.ksat > 0.0) ? 1.0 : ((G / q.ksat < 0.0) ? -1.0 : 0.0);
       const double f = sg / q.ksat;
       const double dG_dhi = -S / (double)nint + qdh * Ahi;
       const double dG_dhf = S / (double)nint + qdh * Ahf;
-      double hi_se, hi_a, hi_n, hi_m, hf_se, hf_a, hf_n, hf_m;
-      h_se_partials(se_i, s, h_i, &hi_se, &hi_a, &hi_n, &hi_m);
-      h_se_partials(se_f, s, h_f, &hf_se, &hf_a, &hf_n, &hf_m);
       const double inv_span = 1.0 / (s.the - s.thr);
       const int ids[5] = {theta_1.id, theta_2.id, s.id_alpha, s.id_n, s.id_m};
-      const double d[5] = {f * (dG_dhi * hi_se + qdh * Csei) * inv_span, f * (dG_dhf * hf_se) * inv_span,
-                           f * (qdh * Ca + dG_dhi * hi_a + dG_dhf * hf_a), f * (qdh * Cn + dG_dhi * hi_n + dG_dhf * hf_n),
-                           f * (qdh * Cm + dG_dhi * hi_m + dG_dhf * hf_m)};
+      const double d[5] = {f * (dG_dhi * pi.a + qdh * Csei) * inv_span, f * (dG_dhf * pf.a) * inv_span,
+                           f * (qdh * Ca + dG_dhi * pi.b + dG_dhf * pf.b), f * (qdh * Cn + dG_dhi * pi.c + dG_dhf * pf.c),
+                           f * (qdh * Cm + dG_dhi * pi.d + dG_dhf * pf.d)};
       result = tape_record_n(value, 5, ids, d);
     }
+    __syncwarp();
   }
+  if (need && ca.st) raise(c, ca.st);
   return result;
 }
 

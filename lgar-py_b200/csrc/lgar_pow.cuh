@@ -113,8 +113,11 @@ LGAR_HD double pow_fma(double a, double b, double c) {
 // then waits out the full FP64 latency of one chain after the other.)  Per element the operations are exactly the
 // same IEEE operations in the same order, so pow_core_v<N> is bit-identical to N scalar calls.
 // Sets ok[k] = false when the arguments are outside the fast path (the caller then uses the library pow).
+// lg (optional): log(x[k]) to double precision -- a by-product of the log stage, used by the derivative weights of
+// the reverse kernel (d x^y / dy = x^y log x) instead of a separate log() call.
 template <int N>
-LGAR_HD void pow_core_v(const double (&x)[N], const double (&y)[N], double (&res)[N], bool (&ok)[N]) {
+LGAR_HD void pow_core_v(const double (&x)[N], const double (&y)[N], double (&res)[N], bool (&ok)[N],
+                        double* lg = nullptr) {
   bool x_ok[N];
   int ki_[N];
   double z[N], kd[N], invc[N], logc[N], logctail[N];
@@ -171,6 +174,9 @@ LGAR_HD void pow_core_v(const double (&x)[N], const double (&y)[N], double (&res
   LGAR_V(lo[e] = ((lo1[e] + lo2[e]) + (lo3[e] + lo4[e])) + (pl[e] + lo5[e]))
   LGAR_V(lhi[e] = hi[e] + lo[e])
   LGAR_V(llo[e] = (hi[e] - lhi[e]) + lo[e])
+  if (lg) {
+    LGAR_V(lg[e] = lhi[e])
+  }
   // ---- ehi + elo = y * log(x)
   LGAR_V(ehi[e] = y[e] * lhi[e])
   LGAR_V(elo[e] = pow_fma(y[e], llo[e], pow_fma(y[e], lhi[e], -ehi[e])))
