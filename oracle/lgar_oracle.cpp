@@ -71,6 +71,7 @@ typedef struct {
   double ksat[LGAR_LMAX];  // already multiplied by frozen_factor (models/dpLGAR.py:57)
   double giuh[LGAR_NGIUH];
   int64_t iter_cap;  // cap for the two root finders (0 -> default 2,000,000)
+  int64_t use_closed_form_G;  // cfg.data.use_closed_form_G (green_ampt.py:85-98)
 } lgar_oracle_cfg;
 }
 
@@ -215,6 +216,7 @@ template <class T>
 struct Soil {  // one layer's parameter set: Layer.attributes + alpha/n/ksat (Layer.py:48-57)
   T alpha, n, ksat, m;
   T theta_e, theta_r;
+  T bc_lambda, bc_psib;  // Brooks-Corey estimates (utils.py:54-99), only read by the closed-form Geff
 };
 
 template <class T>
@@ -265,8 +267,22 @@ static T h_from_se(const T& se, const Soil<T>& s) {  // utils.py:159-174
 // ------------------------------------------------------------------------------------
 // Geff -- physics/lgar/green_ampt.py:19-99 (trapezoid branch; use_closed_form_G=False)
 // ------------------------------------------------------------------------------------
+// closed form (use_closed_form_G=True, green_ampt.py:85-98).  Kept literally, including the swapped roles of
+// theta_1 / theta_2 and the operator precedence of the published line (sic):
+//   geff = h_c * se_i^e - se_f^e / (1 - se_f^e),  e = 3 + 1/lambda;  inf or NaN -> h_c
+template <class T>
+static T calc_geff_closed(const T& theta_1, const T& theta_2, const Soil<T>& s) {
+  T se_f = se_from_theta(theta_1, s);
+  T se_i = se_from_theta(theta_2, s);
+  T h_c = s.bc_psib * (2.0 + 3.0 * s.bc_lambda) / (1.0 + 3.0 * s.bc_lambda);
+  T e = 3.0 + 1.0 / s.bc_lambda;
+  T geff = h_c * safe_pow(se_i, e) - safe_pow(se_f, e) / (1.0 - safe_pow(se_f, e));
+  if (std::isinf(val(geff)) || std::isnan(val(geff))) geff = h_c;
+  return geff;
+}
 template <class T>
 static T calc_geff(const T& theta_1, const T& theta_2, const Soil<T>& s, int nint) {
+  if (nint < 0) return calc_geff_closed(theta_1, theta_2, s);  // nint < 0 encodes use_closed_form_G (see init)
   g_cnt[0]++;
   T se_i = se_from_theta(theta_1, s);
   T se_f = se_from_theta(theta_2, s);
@@ -343,6 +359,7 @@ struct Column {
   //      generate_soil_metrics (data/utils.py:40-105), Layer.__init__ (Layer.py:22-90)
   void init(const lgar_oracle_cfg& c, const T* alpha, const T* n, const T* ksat) {
     cfg = c;
+    if (c.use_closed_form_G) cfg.nint = -1;  // every calc_geff call site passes cfg.nint
     L = c.num_layers;
     iter_cap = c.iter_cap > 0 ? c.iter_cap : 2000000;
     layers.resize(L);
@@ -354,6 +371,13 @@ struct Column {
       ly.s.n = n[l];
       ly.s.ksat = ksat[l];
       ly.s.m = 1.0 - (1.0 / n[l]);  // calc_m utils.py:72-74
+      {  // calc_bc_lambda / calc_bc_psib (utils.py:54-99), as generate_soil_metrics computes them (data/utils.py:85-87)
+        T p_ = 1.0 + (2.0 / ly.s.m);
+        ly.s.bc_lambda = 2.0 / (p_ - 3.0);
+        ly.s.bc_psib = (p_ + 3.0) * (147.8 + 8.1 * p_ + 0.092 * p_ * p_) /
+                       (2.0 * ly.s.alpha * p_ * (p_ - 1.0) * (55.6 + 7.4 * p_ + p_ * p_));
+        if (c.use_closed_form_G) error_check(ly.s.bc_psib);
+      }
       ly.s.theta_e = T(c.theta_e[l]);
       ly.s.theta_r = T(c.theta_r[l]);
       ly.thick = c.thickness[l];

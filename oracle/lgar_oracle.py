@@ -30,6 +30,7 @@ class OracleCfg(C.Structure):
         ("thickness", C.c_double * LMAX), ("theta_r", C.c_double * LMAX),
         ("theta_e", C.c_double * LMAX), ("alpha", C.c_double * LMAX), ("n", C.c_double * LMAX),
         ("ksat", C.c_double * LMAX), ("giuh", C.c_double * NGIUH), ("iter_cap", C.c_int64),
+        ("use_closed_form_G", C.c_int64),
     ]
 
 
@@ -57,12 +58,14 @@ def lib():
 
 def make_cfg(alpha, n, ksat, theta_r, theta_e, thickness=(44.0, 131.0, 25.0), dt_h=1.0,
              num_subcycles=1, initial_psi=2000.0, wilting_point_psi=15495.0, ponded_depth_max=0.0,
-             frozen_factor=1.0, nint=120, giuh=(0.06, 0.51, 0.28, 0.12, 0.03), iter_cap=0) -> OracleCfg:
+             frozen_factor=1.0, nint=120, giuh=(0.06, 0.51, 0.28, 0.12, 0.03), iter_cap=0,
+             use_closed_form_G=False) -> OracleCfg:
     c = OracleCfg()
     L = len(alpha)
     c.num_layers, c.nint, c.num_subcycles, c.num_giuh = L, int(nint), int(num_subcycles), len(giuh)
     c.dt_h, c.initial_psi, c.wilting_point_psi = float(dt_h), float(initial_psi), float(wilting_point_psi)
     c.ponded_depth_max, c.frozen_factor, c.iter_cap = float(ponded_depth_max), float(frozen_factor), int(iter_cap)
+    c.use_closed_form_G = 1 if use_closed_form_G else 0
     for l in range(L):
         c.thickness[l] = float(thickness[l]); c.theta_r[l] = float(theta_r[l]); c.theta_e[l] = float(theta_e[l])
         c.alpha[l] = float(alpha[l]); c.n[l] = float(n[l]); c.ksat[l] = float(ksat[l])
@@ -78,7 +81,8 @@ def cfg_from_golden(g, **over) -> OracleCfg:
         thickness=g["layer_thickness"], dt_h=float(g["subcycle_length_h"]),
         num_subcycles=int(g["num_subcycles"]), initial_psi=float(g["initial_psi"]),
         wilting_point_psi=float(g["wilting_point_psi"]), ponded_depth_max=float(g["ponded_depth_max"]),
-        frozen_factor=float(g["frozen_factor"]), nint=int(g["nint"]), giuh=g["giuh_ordinates"])
+        frozen_factor=float(g["frozen_factor"]), nint=int(g["nint"]), giuh=g["giuh_ordinates"],
+        use_closed_form_G=bool(g["use_closed_form_G"]) if "use_closed_form_G" in g else False)
     kw.update(over)
     return make_cfg(**kw)
 

@@ -86,6 +86,16 @@ def cases():
     c["grad_rand_phil_1"] = dict(
         forcing=(PHIL, 4560, 120), grad=G, alpha=al[9], n=nn[9], ksat=ks[9])
     c["grad_phil_dt300_60"] = dict(forcing=(PHIL, 40, 60), grad=G, cfg=dict(subcycle_length=300.0))
+    # closed-form Green-Ampt capillary drive (cfg.data.use_closed_form_G=True, green_ampt.py:85-98)
+    CF = dict(use_closed_form_G=True)
+    c["closed_phil_4500_400"] = dict(forcing=(PHIL, 4500, 400), cfg=dict(**CF))
+    c["closed_bush_5500_400"] = dict(forcing=(BUSH, 5500, 400), cfg=dict(layer_soil_type=(15, 16, 17), **CF))
+    c["closed_rand_phil_3"] = dict(forcing=(PHIL, 7000, 400), cfg=dict(**CF), alpha=al[11], n=nn[11], ksat=ks[11])
+    c["closed_rand_bush_2"] = dict(forcing=(BUSH, 3300, 400), cfg=dict(layer_soil_type=(15, 16, 17), **CF),
+                                   alpha=al[2], n=nn[2], ksat=ks[2])
+    c["closed_phil_dt300_4560_60"] = dict(forcing=(PHIL, 4560, 60), cfg=dict(subcycle_length=300.0, **CF))
+    c["grad_closed_phil_4550_150"] = dict(forcing=(PHIL, 4550, 150), grad=G, cfg=dict(**CF))
+    c["grad_closed_rand_phil_1"] = dict(forcing=(PHIL, 4560, 120), grad=G, cfg=dict(**CF), alpha=al[9], n=nn[9], ksat=ks[9])
     # columns of the synthetic bench ensemble (lgar_b200.workloads, rank 0, B=16000, T=2560) that reach
     # Layer.wetting_front_cross_domain_boundary (Layer.py:1010-1053) with percolation != 0, and two that
     # die with an AttributeError on a missing neighbour (Q10)
@@ -125,7 +135,7 @@ def run_case(name):
         grad_losses=spec.get("grad"))
     cfg = dict(layer_thickness=(44.0, 131.0, 25.0), ponded_depth_max=0.0, subcycle_length=3600.0,
                forcing_resolution=3600.0, initial_psi=2000.0, wilting_point_psi=15495.0,
-               nint=120, frozen_factor=1.0, giuh_ordinates=(0.06, 0.51, 0.28, 0.12, 0.03))
+               nint=120, frozen_factor=1.0, giuh_ordinates=(0.06, 0.51, 0.28, 0.12, 0.03), use_closed_form_G=False)
     cfg.update({k: v for k, v in (spec.get("cfg") or {}).items() if k in cfg})
     r["layer_thickness"] = np.array(cfg["layer_thickness"], dtype=np.float64)
     r["theta_r"] = r["c"][:, 0].copy()
@@ -135,6 +145,7 @@ def run_case(name):
     r["wilting_point_psi"] = float(cfg["wilting_point_psi"])
     r["nint"] = int(cfg["nint"])
     r["frozen_factor"] = float(cfg["frozen_factor"])
+    r["use_closed_form_G"] = bool(cfg["use_closed_form_G"])
     r["giuh_ordinates"] = np.array(cfg["giuh_ordinates"], dtype=np.float64)
     r["subcycle_length_h"] = cfg["subcycle_length"] * (1 / 3600.0)
     r["num_subcycles"] = int((cfg["forcing_resolution"] / 3600.0) / r["subcycle_length_h"])
