@@ -99,7 +99,8 @@ typedef struct lgar_problem {
                               1: continue from the column state the previous lgar_forward left in
                               this workspace (same B, L, max_fronts; keep_checkpoints == 0): lets a
                               caller advance one forcing row per call like dpLGAR.forward(x)         */
-  int32_t reserved1;
+  int32_t use_closed_form_G; /* cfg.data.use_closed_form_G: 0 = trapezoid Geff (green_ampt.py:45-84),
+                              1 = Brooks-Corey closed form (green_ampt.py:85-98); was reserved (0) before   */
   int64_t iter_cap;        /* root-finder iteration cap (0 = default 1,000,000)                 */
   double subcycle_length_h;   /* dt in hours                 cfg.models.subcycle_length_h       */
   double wilting_point_psi;   /* cm                          cfg.data.wilting_point_psi         */

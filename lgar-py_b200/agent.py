@@ -35,7 +35,7 @@ def _get(cfg, path, default=None):
     for key in path.split("."):
         if cur is None:
             return default
-        cur = cur[key] if isinstance(cur, dict) else getattr(cur, key, None)
+        cur = cur.get(key) if isinstance(cur, dict) else getattr(cur, key, None)
     return default if cur is None else cur
 
 
@@ -191,6 +191,12 @@ class DifferentiableLGAR:
         """One pass over the record(s): one forward launch, mass-balance report, then `validate()`."""
         self.optimizer.zero_grad()
         out = self.model.forward_record(self.x if self.x.shape[0] > 1 else self.x[0], outputs=self.OUTPUTS)
+        st = out.get("status")
+        if st is not None and bool((st != 0).any()):  # the reference raises out of model(x) (SURVEY Q9-Q11)
+            from ._capi import STATUS_NAMES
+            bad = int(st.reshape(-1)[(st.reshape(-1) != 0).nonzero()[0, 0]])
+            step = int(out["crash_step"].reshape(-1)[(st.reshape(-1) != 0).nonzero()[0, 0]])
+            raise RuntimeError(f"LGAR column status {STATUS_NAMES[bad]} at forcing step {step} (the reference raises here)")
         self._report_mass(out)
         y_hat = out["runoff"]
         if y_hat.dim() == 1:

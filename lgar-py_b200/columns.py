@@ -51,6 +51,7 @@ class ColumnEnsemble:
     nint: int = 120
     wilting_point_psi: float = 15495.0
     frozen_factor: float = 1.0
+    use_closed_form_G: bool = False  # cfg.data.use_closed_form_G (green_ampt.py:85-98)
     giuh_ordinates: Sequence[float] = (0.06, 0.51, 0.28, 0.12, 0.03)
     max_fronts: int = 16
     chunk_steps: int = 64
@@ -94,6 +95,7 @@ class ColumnEnsemble:
         p.nint, p.num_giuh = int(self.nint), len(self.giuh_ordinates)
         p.max_fronts, p.chunk_steps, p.iter_cap = int(self.max_fronts), int(self.chunk_steps), int(self.iter_cap)
         p.resume = 1 if self.resume else 0
+        p.use_closed_form_G = 1 if self.use_closed_form_G else 0
         p.subcycle_length_h = float(self.subcycle_length_h)
         p.wilting_point_psi = float(self.wilting_point_psi)
         p.frozen_factor = float(self.frozen_factor)

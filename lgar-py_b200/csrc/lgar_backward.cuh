@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(NT) lgar_backward_kernel(const BParams P) {
         Var mV = 1.0 - (1.0 / Var(sl.n, sl.id_n));
         sl.id_m = mV.id;
       }
-      init_column(Tv, __ldg(p.initial_psi + bb));
+      init_column(Tv, __ldg(p.initial_psi + bb), p.use_closed_form_G != 0);
       const int ne = min(tc.n, tc.cap);
       if (valid && Tv.ctx.st == 0) {
         for (int q = 0; q < NL + ne; q++) adj[(size_t)q * 32] = 0.0;

@@ -507,6 +507,85 @@ __device__ __forceinline__ double geff_warp(bool need, double theta_1, double th
 }
 
 // ------------------------------------------------------------------------------------
+// Closed-form capillary drive (cfg.data.use_closed_form_G, green_ampt.py:85-98), per lane (three pows, no warp
+// cooperation needed).  Literal restatement, including the swapped roles of theta_1 / theta_2 and the operator
+// precedence of the published line (sic):
+//   se_f = Se(theta_1), se_i = Se(theta_2);  h_c = psib (2 + 3 lambda) / (1 + 3 lambda);  e = 3 + 1 / lambda
+//   geff = h_c * se_i^e - se_f^e / (1 - se_f^e);  inf or NaN -> h_c
+// with the Brooks-Corey estimates of generate_soil_metrics (data/utils.py:85-87, utils.py:54-99):
+//   p = 1 + 2/m;  lambda = 2 / (p - 3);  psib = (p + 3)(147.8 + 8.1 p + 0.092 p^2) / (2 alpha p (p - 1)(55.6 + 7.4 p + p^2))
+// P == true also returns the partials w.r.t. theta_1, theta_2, alpha and m (reference autograd: gradient flows
+// through lambda(m) and psib(alpha, m); torch's pow has zero exponent-gradient at base 0).
+// Selected by nint < 0 at the geff_warpR call sites (substep passes nint = -1 when the flag is set).
+// ------------------------------------------------------------------------------------
+struct GeffClosed {
+  double v, d_t1, d_t2, d_alpha, d_m;
+  int st;
+};
+__device__ __forceinline__ double bc_psib(double alpha, double m) {
+  const double p_ = 1.0 + (2.0 / m);
+  return (p_ + 3.0) * (147.8 + 8.1 * p_ + 0.092 * p_ * p_) / (2.0 * alpha * p_ * (p_ - 1.0) * (55.6 + 7.4 * p_ + p_ * p_));
+}
+template <bool P>
+__device__ __noinline__ GeffClosed geff_closed_core(double theta_1, double theta_2, double alpha, double m, double the,
+                                                    double thr) {
+  GeffClosed r;
+  r.v = r.d_t1 = r.d_t2 = r.d_alpha = r.d_m = 0.0;
+  int st = 0;
+  const double span = the - thr;
+  const double se_f = (theta_1 - thr) / span;
+  if (isnan(se_f)) st = LGAR_ST_NAN;
+  const double se_i = (theta_2 - thr) / span;
+  if (!st && isnan(se_i)) st = LGAR_ST_NAN;
+  const double p_ = 1.0 + (2.0 / m);
+  const double lam = 2.0 / (p_ - 3.0);
+  const double psib = bc_psib(alpha, m);
+  const double h_c = psib * (2.0 + 3.0 * lam) / (1.0 + 3.0 * lam);
+  const double e = 3.0 + 1.0 / lam;
+  // safe_pow guards (utils.py:12-32) in call order: se_i^e, se_f^e, se_f^e
+  if (!st) st = (isnan(se_i) || isnan(e)) ? LGAR_ST_NAN : (se_i < 0.0 ? LGAR_ST_NEG_POW : 0);
+  if (!st) st = isnan(se_f) ? LGAR_ST_NAN : (se_f < 0.0 ? LGAR_ST_NEG_POW : 0);
+  double A, Bq, lse_i = 0.0, lse_f = 0.0;
+  if (P) {
+    const double2 a = pow_log_f64(se_i, e), b = pow_log_f64(se_f, e);
+    A = a.x; lse_i = a.y; Bq = b.x; lse_f = b.y;
+  } else {
+    const double2 ab = pow_x2(se_i, e, se_f, e);
+    A = ab.x; Bq = ab.y;
+  }
+  const double D = 1.0 - Bq;
+  double geff = h_c * A - Bq / D;
+  const bool fallback = isinf(geff) || isnan(geff);
+  if (fallback) geff = h_c;
+  r.v = geff;
+  r.st = st;
+  if (P) {
+    const double dg_dhc = fallback ? 1.0 : A;
+    double dg_de = 0.0;
+    if (!fallback) {
+      dg_de = ((se_i == 0.0) ? 0.0 : h_c * A * lse_i) - ((se_f == 0.0) ? 0.0 : Bq * lse_f / (D * D));
+      r.d_t2 = ((se_i == 0.0) ? 0.0 : h_c * e * A / se_i) / span;
+      r.d_t1 = -((se_f == 0.0) ? 0.0 : (e * Bq / se_f) / (D * D)) / span;
+    }
+    const double q3 = 1.0 + 3.0 * lam;
+    const double dhc_dpsib = (2.0 + 3.0 * lam) / q3;
+    const double dhc_dlam = -3.0 * psib / (q3 * q3);
+    const double de_dlam = -1.0 / (lam * lam);
+    const double dlam_dp = -2.0 / ((p_ - 3.0) * (p_ - 3.0));
+    const double dp_dm = -2.0 / (m * m);
+    const double N1 = p_ + 3.0, N2 = 147.8 + 8.1 * p_ + 0.092 * p_ * p_;
+    const double D3 = 55.6 + 7.4 * p_ + p_ * p_;
+    const double dlnN = 1.0 / N1 + (8.1 + 0.184 * p_) / N2;
+    const double dlnD = 1.0 / p_ + 1.0 / (p_ - 1.0) + (7.4 + 2.0 * p_) / D3;
+    const double dpsib_dp = psib * (dlnN - dlnD);
+    const double dg_dlam = dg_dhc * dhc_dlam + dg_de * de_dlam;
+    r.d_alpha = dg_dhc * dhc_dpsib * (-psib / alpha);
+    r.d_m = (dg_dhc * dhc_dpsib * dpsib_dp + dg_dlam * dlam_dp) * dp_dm;
+  }
+  return r;
+}
+
+// ------------------------------------------------------------------------------------
 // Scalar-generic layer: R = double (forward kernel) or R = Var (taped pass of the reverse kernel).
 // ------------------------------------------------------------------------------------
 template <class R>
@@ -662,6 +741,12 @@ __device__ __forceinline__ Pair<Var> psi_kR(const Var& se, const SoilT<Var>& s, 
 //      d geff / d ksat = 0 (K is proportional to ksat).
 __device__ __forceinline__ double geff_warpR(bool need, double theta_1, double theta_2, const SoilT<double>& s, int nint,
                                             double* nodebuf, Ctx& c) {
+  if (nint < 0) {  // closed form (warp-uniform switch)
+    if (!need) return 0.0;
+    const GeffClosed g = geff_closed_core<false>(theta_1, theta_2, s.alpha, s.m, s.the, s.thr);
+    if (g.st) raise(c, g.st);
+    return g.v;
+  }
   return geff_warp(need, theta_1, theta_2, s, nint, nodebuf, c);
 }
 __device__ __forceinline__ double warp_sum(double v) {
@@ -734,6 +819,14 @@ __device__ __noinline__ NodeFull k_node_full(double h, bool node0, double se0, d
 // pows per node for the value AND the partials (a separate partial pass cost four more pows and four logs).
 __device__ Var geff_warpR(bool need, const Var& theta_1, const Var& theta_2, const SoilT<Var>& s, int nint,
                           double* nodebuf, Ctx& c) {
+  if (nint < 0) {  // closed form (warp-uniform switch): one tape entry with four partials
+    if (!need) return Var(0.0);
+    const GeffClosed g = geff_closed_core<true>(theta_1.v, theta_2.v, s.alpha, s.m, s.the, s.thr);
+    if (g.st) raise(c, g.st);
+    const int ids[4] = {theta_1.id, theta_2.id, s.id_alpha, s.id_m};
+    const double d[4] = {g.d_t1, g.d_t2, g.d_alpha, g.d_m};
+    return tape_record_n(g.v, 4, ids, d);
+  }
   const int lane = threadIdx.x & 31;
   // stage A: the scalars of geff_warp_core, plus the end-point partials of h(Se) for every requesting lane at once
   Ctx ca;

@@ -82,13 +82,14 @@ __device__ __forceinline__ R calc_aet(Tile<FM, R>& T, double pet, double dt) {
 // set_internal_states (models/dpLGAR.py:97-147), Layer.__init__ (Layer.py:22-90),
 // WettingFront.__init__ (WettingFront.py:18-49), generate_soil_metrics (data/utils.py:40-105)
 template <int FM, class R>
-__device__ void init_column(Tile<FM, R>& T, double initial_psi) {
+__device__ void init_column(Tile<FM, R>& T, double initial_psi, bool closed_form_G = false) {
   Column<FM, R>& C = T.col;
   Ctx& c = T.ctx;
   C.n = 0;
   C.cntpk = 0;
   for (int l = 0; l < C.L; l++) {
     const SoilT<R>& s = C.soil[l];
+    if (closed_form_G && isnan(bc_psib(s.alpha, s.m))) raise(c, LGAR_ST_NAN);  // error_check in calc_bc_psib (utils.py:99)
     R theta_init = thetaR(R(initial_psi), s, c);
     const int i = C.n;
     C.s(F_DEPTH, i, R(C.cum[l]));
@@ -116,7 +117,7 @@ __device__ void substep(Tile<FM, R>& T, bool act, double precip_rate, double pet
   Column<FM, R>& C = T.col;
   Ctx& c = T.ctx;
   const double dt = K.p.subcycle_length_h;
-  const int nint = K.p.nint;
+  const int nint = K.p.use_closed_form_G ? -1 : K.p.nint;  // nint < 0 selects the closed-form Geff (geff_warpR)
   const int L = C.L;
   act = act && (c.st == 0);
 
@@ -476,7 +477,7 @@ __global__ void __launch_bounds__(NT, (FM == 16) ? 2 : ((FM == 12) ? 3 : 4)) lga
     } else if (chunk == 0) {
       T.ctx.st = 0;
       T.crash_step = -1;
-      init_column(T, __ldg(p.initial_psi + bb));
+      init_column(T, __ldg(p.initial_psi + bb), p.use_closed_form_G != 0);
       if (T.ctx.st) T.crash_step = 0;
       if (valid && K.o.start_volume) K.o.start_volume[b] = T.col.ending_volume;
       if (K.keep_ckpt && valid) save_state(K, 0, b, T);

@@ -4,7 +4,7 @@ Mirrors the public surface of dpLGAR/models/dpLGAR.py:30-430 that its callers us
 (agents/DifferentiableLGAR.py:63-171, models/physics/MassBalance.py:31-108):
 
   * ctor `dpLGAR(cfg)`: the same cfg keys: cfg.data.{layer_soil_type, layer_thickness, initial_psi,
-    ponded_depth_max, wilting_point_psi, giuh_ordinates, soil_params_file}, cfg.constants.{frozen_factor, nint},
+    ponded_depth_max, wilting_point_psi, giuh_ordinates, soil_params_file, use_closed_form_G}, cfg.constants.{frozen_factor, nint},
     cfg.models.{subcycle_length_h, num_subcycles}; cfg may be an omegaconf DictConfig or any attribute/dict mapping;
   * parameters `.alpha/.n/.ksat` = nn.ParameterList of 0-dim float64 (initial values: the reference's
     read_test_params table, data/utils.py:108-180, rows = cfg.data.layer_soil_type, ksat * frozen_factor);
@@ -46,7 +46,7 @@ def _get(cfg, path, default=None):
     for key in path.split("."):
         if cur is None:
             return default
-        cur = cur[key] if isinstance(cur, dict) else getattr(cur, key, None)
+        cur = cur.get(key) if isinstance(cur, dict) else getattr(cur, key, None)
     return default if cur is None else cur
 
 
@@ -89,7 +89,8 @@ class dpLGAR(nn.Module):
         self._ens_kw = dict(
             initial_psi=float(_get(cfg, "data.initial_psi", 2000.0)), ponded_depth_max=float(self.ponded_depth_max),
             subcycle_length_h=self.dt_h, num_subcycles=self.num_subcycles, nint=int(_get(cfg, "constants.nint", 120)),
-            wilting_point_psi=float(_get(cfg, "data.wilting_point_psi", 15495.0)), frozen_factor=ff, giuh_ordinates=giuh)
+            wilting_point_psi=float(_get(cfg, "data.wilting_point_psi", 15495.0)), frozen_factor=ff, giuh_ordinates=giuh,
+            use_closed_form_G=bool(_get(cfg, "data.use_closed_form_G", False)))
         self._step_ens = None
         self._ws = None
         self.set_internal_states()

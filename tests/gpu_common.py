@@ -16,7 +16,8 @@ def ensemble_from_golden(g, copies=1, **over):
         ponded_depth_max=float(g["ponded_depth_max"]), subcycle_length_h=float(g["subcycle_length_h"]),
         num_subcycles=int(g["num_subcycles"]), nint=int(g["nint"]),
         wilting_point_psi=float(g["wilting_point_psi"]), frozen_factor=float(g["frozen_factor"]),
-        giuh_ordinates=tuple(float(x) for x in g["giuh_ordinates"]))
+        giuh_ordinates=tuple(float(x) for x in g["giuh_ordinates"]),
+        use_closed_form_G=bool(g["use_closed_form_G"]) if "use_closed_form_G" in g else False)
     kw.update(over)
     ens = ColumnEnsemble(**kw)
     return ens, rep(g["alpha"]), rep(g["n"]), rep(g["ksat"])
