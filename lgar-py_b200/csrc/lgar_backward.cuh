@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(NT) lgar_backward_kernel(const BParams P) {
           if (x.y > 0.0) precompute_psi_wp(Tv, p.wilting_point_psi);
 #pragma unroll
           for (int k = 0; k < NOUT; k++) Tv.acc[k] = Var(0.0);
-          substep(Tv, alive, x.x, x.y, K, nodebuf);
+          substep<FM, Var, 2>(Tv, alive, x.x, x.y, K, nodebuf);
           __syncwarp();
           if (tc.n > tc.cap) overflow = true;
           const int ne = min(tc.n, tc.cap);

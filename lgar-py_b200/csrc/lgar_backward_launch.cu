@@ -1,11 +1,8 @@
 // =====================================================================================
 // lgar_backward_launch.cu -- the reverse-mode kernel's own translation unit.
-// Compiled separately from lgar_capi.cu (forward kernel) so that the two kernels can make different
-// shared-memory trade-offs: the reverse kernel needs every byte of its 2-CTAs-per-SM budget for the value +
-// tape-id arrays and therefore keeps the pow tables in global memory (L1), the forward kernel copies them
-// to shared memory.  Also halves the build time (the two units compile in parallel).
+// Compiled separately from lgar_capi.cu (forward kernel): the two units compile in parallel (half the build time)
+// and can make different code-generation trade-offs (e.g. pow-table placement, see lgar_pow.cuh).
 // =====================================================================================
-#define LGAR_POW_TABLES_GLOBAL 1
 // every header symbol of this unit lives in its own namespace: the host-side stubs of the __device__ functions
 // would otherwise collide with the forward unit's at link time (and the two units compile them differently)
 #define lgar lgar_reverse_unit

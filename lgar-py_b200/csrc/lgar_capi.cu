@@ -229,7 +229,8 @@ int lgar_forward(const lgar_problem* p, const lgar_outputs* out, void* workspace
   if (out->counters) CUDA_TRY(cudaMemsetAsync(out->counters, 0, 8 * sizeof(unsigned long long), st));
   if (out->tile_cycles)
     CUDA_TRY(cudaMemsetAsync(out->tile_cycles, 0, (size_t)s.ntiles * sizeof(unsigned long long), st));
-  const bool count = out->counters != nullptr;
+  // the kernels without work counters are trapezoid-only (closed-form branch compiled out of the hot path)
+  const bool count = out->counters != nullptr || p->use_closed_form_G != 0;
   const bool dump = out->fronts != nullptr;
   if (dump && s.FM != 16) return fail(LGAR_E_INVALID, "front dumps need max_fronts = 16");
 #define LGAR_DISPATCH(FM_)                                                         \

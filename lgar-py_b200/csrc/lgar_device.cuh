@@ -31,11 +31,7 @@ namespace lgar {
 
 constexpr int NT = 128;          // threads per CTA (4 warps, each warp an independent tile)
 constexpr int WARPS = NT / 32;
-#ifdef LGAR_DENSE_ROOT_EVAL
-constexpr int NODEBUF = 192;     // doubles of per-warp scratch: Geff nodes (nint <= 128) / dense theta(h) work queue (3 x 64)
-#else
 constexpr int NODEBUF = 136;     // doubles of per-warp scratch for Geff nodes (nint <= 128)
-#endif
 constexpr int MAXL = LGAR_MAX_LAYERS;
 constexpr int NGIUH = LGAR_MAX_GIUH;
 constexpr int NOUT = LGAR_NUM_OUTPUTS;
@@ -88,6 +84,7 @@ __device__ __noinline__ double2 pow_log_f64(double a, double b) {
 }
 // two INDEPENDENT pows issued interleaved from one basic block (ILP: pow is one long dependent chain)
 __device__ __noinline__ double2 pow_x2(double x0, double y0, double x1, double y1) {
+#ifdef LGAR_POW_X2_VECTOR
   const double xv[2] = {x0, x1}, yv[2] = {y0, y1};
   double r[2];
   bool ok[2];
@@ -95,6 +92,14 @@ __device__ __noinline__ double2 pow_x2(double x0, double y0, double x1, double y
   if (!ok[0]) r[0] = pow_slow(x0, y0);
   if (!ok[1]) r[1] = pow_slow(x1, y1);
   return make_double2(r[0], r[1]);
+#else
+  bool ok0, ok1;
+  double a = pow_core(x0, y0, ok0);
+  double b = pow_core(x1, y1, ok1);
+  if (!ok0) a = pow_slow(x0, y0);
+  if (!ok1) b = pow_slow(x1, y1);
+  return make_double2(a, b);
+#endif
 }
 
 struct D4 {
@@ -282,7 +287,9 @@ __device__ __noinline__ double advance_rounded_pos(double x, double s, long long
     const double lim = (s > 0.0) ? __hiloint2double((e1 + 1) << 20, 0) : __hiloint2double(e1 << 20, 0);
     const double room = (s > 0.0) ? (lim - t) : (t - lim);
     // common case: all remaining steps fit ((k + 1) |c| <= room, tested conservatively) -- no division
+#ifndef LGAR_ADV_OLD
     if ((double)(k + 1) * fabs(c) * (1.0 + 0x1p-40) <= room) return fma((double)k, c, t);
+#endif
     long long n = (long long)floor(room / fabs(c)) - 1;
     if (n > k) n = k;
     if (n < 0) n = 0;
@@ -299,81 +306,7 @@ __device__ __forceinline__ double advance_rounded(double x, double s, long long 
   return neg ? -r : r;
 }
 
-// ------------------------------------------------------------------------------------
-// Dense theta(h) evaluation for DIVERGENT callers (the root finder of the move sweep: typically a third of
-// the lanes are still iterating, each with 1 + nup <= MAXL evaluations).  The FP64 pipe is occupied for the
-// same two cycles per warp instruction whether 1 or 32 lanes are active (tools/pow_ilp_microbench.cu: the pow
-// code is pipe-bound at 2 warps per sub-partition), so the requests of all lanes are compacted into a per-warp
-// queue in shared memory and evaluated by ALL lanes: item = (x = alpha h, n, m) -> (1 + x^n)^m, i.e. the two
-// pows of utils.py:35-51; the owner applies the affine tail and the guards itself, so the values are
-// bit-identical to theta_h_core().  Rounds of 64 items; a round of <= 32 items takes the single-chain path.
-// Must be called by all 32 lanes (convergent).  wq: per-warp scratch of >= 192 doubles (the Geff node buffer).
-// MEASURED (B200, 125000 x 128): 200 ms against 171 ms for the per-lane pair evaluation -- with two warps per
-// sub-partition the root finder is bound by the LATENCY of two dependent pows per pass, not by pipe slots, so
-// compaction buys nothing and the queue traffic costs.  Kept behind LGAR_DENSE_ROOT_EVAL (off) for a future
-// variant that fills the idle slots with speculative iterations.
-// ------------------------------------------------------------------------------------
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-#ifdef LGAR_DENSE_ROOT_EVAL
-__device__ __noinline__ D4 theta_outer_dense(int cnt, double x0, double n0, double m0, double x1, double n1, double m1,
-                                              double x2, double n2, double m2, double x3, double n3, double m3,
-                                              double* wq) {
-  const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const unsigned lt = (1u << lane) - 1u;
-  const unsigned b1 = __ballot_sync(FULL, cnt & 1), b2 = __ballot_sync(FULL, cnt & 2), b4 = __ballot_sync(FULL, cnt & 4);
-  const int base = __popc(b1 & lt) + 2 * __popc(b2 & lt) + 4 * __popc(b4 & lt);
-  const int total = __popc(b1) + 2 * __popc(b2) + 4 * __popc(b4);
-  D4 out;
-  out.a = out.b = out.c = out.d = 0.0;
-  for (int r0 = 0; r0 < total; r0 += 64) {
-    const int nr = min(64, total - r0);
-    // owners publish their items of this round
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int slot = base + k - r0;
-      if (k < cnt && slot >= 0 && slot < 64) {
-        wq[slot] = (k == 0) ? x0 : ((k == 1) ? x1 : ((k == 2) ? x2 : x3));
-        wq[64 + slot] = (k == 0) ? n0 : ((k == 1) ? n1 : ((k == 2) ? n2 : n3));
-        wq[128 + slot] = (k == 0) ? m0 : ((k == 1) ? m1 : ((k == 2) ? m2 : m3));
-      }
-    }
-    __syncwarp();
-    if (nr <= 32) {
-      double o = 0.0;
-      if (lane < nr) {
-        const double m = wq[128 + lane];
-        o = pow_f64(1.0 + pow_f64(wq[lane], wq[64 + lane]), m);
-      }
-      __syncwarp();
-      if (lane < nr) wq[lane] = o;
-    } else {
-      const bool hb = lane + 32 < nr;  // lane always owns slot `lane` here
-      const double xa = wq[lane], na = wq[64 + lane], ma = wq[128 + lane];
-      const double xb = hb ? wq[lane + 32] : 1.0, nb = hb ? wq[96 + lane] : 1.0, mb = hb ? wq[160 + lane] : 1.0;
-      const double2 p = pow_x2(xa, na, xb, nb);
-      const double2 q = pow_x2(1.0 + p.x, ma, 1.0 + p.y, mb);
-      __syncwarp();
-      wq[lane] = q.x;
-      if (hb) wq[lane + 32] = q.y;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int slot = base + k - r0;
-      if (k < cnt && slot >= 0 && slot < 64) {
-        const double v = wq[slot];
-        if (k == 0) out.a = v;
-        else if (k == 1) out.b = v;
-        else if (k == 2) out.c = v;
-        else out.d = v;
-      }
-    }
-    __syncwarp();
-  }
-  return out;
-}
-#endif
 
 // torch.min / torch.minimum semantics (NaN propagates, unlike fmin)
 __device__ __forceinline__ double tmin(double a, double b) {
@@ -739,9 +672,12 @@ __device__ __forceinline__ Pair<Var> psi_kR(const Var& se, const SoilT<Var>& s, 
 // ---- Geff: value from the forward routine (bit-identical), partials cooperatively (lanes = nodes).
 //      G = dh sum_k w_k K_k, geff = |G / ksat|; K_k = K(Se(h_k)), h_k = h_i + k dh, node 0 uses K(Se_i).
 //      d geff / d ksat = 0 (K is proportional to ksat).
+// GM (Geff mode) = 0: trapezoid only (the production forward kernel: the closed-form branch is compiled out of
+// its three call sites); GM = 2: run-time switch, nint < 0 selects the closed form.
+template <int GM>
 __device__ __forceinline__ double geff_warpR(bool need, double theta_1, double theta_2, const SoilT<double>& s, int nint,
                                             double* nodebuf, Ctx& c) {
-  if (nint < 0) {  // closed form (warp-uniform switch)
+  if (GM == 2 && nint < 0) {  // closed form (warp-uniform switch)
     if (!need) return 0.0;
     const GeffClosed g = geff_closed_core<false>(theta_1, theta_2, s.alpha, s.m, s.the, s.thr);
     if (g.st) raise(c, g.st);
@@ -817,9 +753,10 @@ __device__ __noinline__ NodeFull k_node_full(double h, bool node0, double se0, d
 
 // Fused value + gradient pass of the reverse kernel: the node loop of geff_warp_core with k_node_full, i.e. four
 // pows per node for the value AND the partials (a separate partial pass cost four more pows and four logs).
+template <int GM>
 __device__ Var geff_warpR(bool need, const Var& theta_1, const Var& theta_2, const SoilT<Var>& s, int nint,
                           double* nodebuf, Ctx& c) {
-  if (nint < 0) {  // closed form (warp-uniform switch): one tape entry with four partials
+  if (GM == 2 && nint < 0) {  // closed form (warp-uniform switch): one tape entry with four partials
     if (!need) return Var(0.0);
     const GeffClosed g = geff_closed_core<true>(theta_1.v, theta_2.v, s.alpha, s.m, s.the, s.thr);
     if (g.st) raise(c, g.st);
@@ -1161,7 +1098,7 @@ struct Column {
   enum Kind { K_NONE = 0, K_DEEPEST = 1, K_INLAYER0 = 2, K_INLAYER_DEEP = 3, K_BASE = 4 };
 
   __device__ void move_wetting_fronts_warp(bool go, int fd, const R& infiltration, const R& aet, const R& old_mass,
-                                           double dt, Ctx& c, double* wq) {
+                                           double dt, Ctx& c) {
     const unsigned FULL = 0xffffffffu;
     go = go && (c.st == 0);
     const int num_wf = go ? n : 0;
@@ -1323,14 +1260,15 @@ struct Column {
               active = false;
             }
           }
-          // ---- propose the next psi (per lane)
-          bool probe = false, up = false, sw = switched;
-          double step = 0.0, psi_try = 1.0, psi_prev_try = psi_prev;
-          double scale_try = psi_scale, prev_scale_try = prev_scale, fac = factor;
           if (active) {
             c.cnt[C_ROOT]++;
-            probe = stride >= 2;
-            up = probe ? run_up : (new_mass > prior_mass);
+            const bool probe = stride >= 2;
+            const bool up = probe ? run_up : (new_mass > prior_mass);
+            double step;
+            double psi_try, psi_prev_try = psi_prev;
+            double scale_try = psi_scale, prev_scale_try = prev_scale;
+            bool sw = switched;
+            double fac = factor;
             if (probe) {
               if (pred) fac = factor * 0.1;  // the first step of a down-run after an up-step shrinks the factor
               step = 0.1 * fac;
@@ -1355,39 +1293,6 @@ struct Column {
                 scale_try = prev_scale_try * 0.1;
               }
             }
-          }
-#ifdef LGAR_DENSE_ROOT_EVAL
-          // ---- evaluate theta_k(psi_try) in the front's layer and the layers above: the requests of all
-          //      iterating lanes are compacted and evaluated by the whole warp (theta_outer_dense)
-          const int nev = active ? 1 + nup : 0;
-          const D4 od = theta_outer_dense(nev, own.alpha * psi_try, own.n, own.m, up0.alpha * psi_try, up0.n, up0.m,
-                                          up1.alpha * psi_try, up1.n, up1.m,
-                                          soil[(MAXL > 3) ? 2 : 0].alpha * psi_try, soil[(MAXL > 3) ? 2 : 0].n,
-                                          soil[(MAXL > 3) ? 2 : 0].m, wq);
-          if (active) {
-            Ctx cc;  // guards raised by a rejected probe must not kill the column
-            cc.st = 0;
-            // guards in the order of theta_from_h_x2(own, up0) followed by theta_from_h(up1), ... (utils.py:12-51)
-            guard_pow(own.alpha * psi_try, own.n, cc);
-            if (nup > 0) guard_pow(up0.alpha * psi_try, up0.n, cc);
-            const double th = (1.0 / od.a * (own.the - own.thr)) + own.thr;
-            const double th_up0 = (1.0 / od.b * (up0.the - up0.thr)) + up0.thr;
-            if (isnan(th) || (nup > 0 && isnan(th_up0))) raise(cc, LGAR_ST_NAN);
-            double mass_layers = 0.0 + (own_dtk * (th - own_dth));
-            if (nup > 0) mass_layers = mass_layers + dtk[0] * (th_up0 - dth[0]);
-            if (nup > 1) {
-              guard_pow(up1.alpha * psi_try, up1.n, cc);
-              const double theta_layer = error_check((1.0 / od.c * (up1.the - up1.thr)) + up1.thr, cc);
-              mass_layers = mass_layers + dtk[1] * (theta_layer - dth[1]);
-            }
-            if (MAXL > 3 && nup > 2) {
-              const Soil& s2 = soil[(MAXL > 3) ? 2 : 0];
-              guard_pow(s2.alpha * psi_try, s2.n, cc);
-              const double theta_layer = error_check((1.0 / od.d * (s2.the - s2.thr)) + s2.thr, cc);
-              mass_layers = mass_layers + dtk[(MAXL > 3) ? 2 : 0] * (theta_layer - dth[(MAXL > 3) ? 2 : 0]);
-            }
-#else
-          if (active) {
             Ctx cc;  // guards raised by a rejected probe must not kill the column
             cc.st = 0;
             cc.cnt[C_THETA_H] = 0;
@@ -1407,8 +1312,7 @@ struct Column {
                 mass_layers = mass_layers + dtk[k] * (theta_layer - dth[k]);
               }
             }
-#endif
-            c.cnt[C_THETA_H] += 1 + nup;
+            c.cnt[C_THETA_H] += cc.cnt[C_THETA_H];
             const double dm = fabs(mass_layers - prior_mass);
             if (probe) {
               const bool cont = up ? (mass_layers > prior_mass) : (mass_layers <= prior_mass);
@@ -1809,8 +1713,8 @@ struct Column {
   // ---- dpLGAR.move_wetting_front (models/dpLGAR.py:340-367); returns the bottom flux.
   //      Warp-convergent (every lane calls; `go` selects the lanes that actually move fronts).
   __device__ R move_wetting_front_warp(bool go, int fd, const R& infiltration, R& AET_sub, const R& old_mass, double dt,
-                                       Ctx& c, double* wq) {
-    move_wetting_fronts_warp(go, fd, infiltration, AET_sub, old_mass, dt, c, wq);
+                                       Ctx& c) {
+    move_wetting_fronts_warp(go, fd, infiltration, AET_sub, old_mass, dt, c);
     R bottom_flux(0.0);
     if (go && c.st == 0) {
       merge_wetting_fronts(c);

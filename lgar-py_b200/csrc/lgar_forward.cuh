@@ -111,13 +111,13 @@ __device__ void init_column(Tile<FM, R>& T, double initial_psi, bool closed_form
 
 // ---- one sub-step: models/dpLGAR.py:176-298.  Warp-convergent: every lane of the warp calls it;
 //      lanes with act == false only take part in the cooperative Geff evaluations.
-template <int FM, class R>
+template <int FM, class R, int GM>
 __device__ void substep(Tile<FM, R>& T, bool act, double precip_rate, double pet_rate, const KParams& K,
                         double* nodebuf) {
   Column<FM, R>& C = T.col;
   Ctx& c = T.ctx;
   const double dt = K.p.subcycle_length_h;
-  const int nint = K.p.use_closed_form_G ? -1 : K.p.nint;  // nint < 0 selects the closed-form Geff (geff_warpR)
+  const int nint = (GM == 2 && K.p.use_closed_form_G) ? -1 : K.p.nint;  // nint < 0 selects the closed-form Geff (geff_warpR)
   const int L = C.L;
   act = act && (c.st == 0);
 
@@ -159,7 +159,7 @@ __device__ void substep(Tile<FM, R>& T, bool act, double precip_rate, double pet
         theta_2 = R(C.soil[lfp].the);
       }
     }
-    const R geff = geff_warpR(needG, theta_1, theta_2, C.soil[needG ? lfp : 0], nint, nodebuf, c);
+    const R geff = geff_warpR<GM>(needG, theta_1, theta_2, C.soil[needG ? lfp : 0], nint, nodebuf, c);
     if (brB && c.st == 0) {
       const R h_p = clamp_min_((ponded_depth_sub - precip_sub) * dt, 0.0);  // clamp(min=0)
       const R fd_depth = C.g(F_DEPTH, fd);
@@ -207,7 +207,7 @@ __device__ void substep(Tile<FM, R>& T, bool act, double precip_rate, double pet
   {
     const bool go = act && c.st == 0 && (brA || !create);
     const R infil_arg = create ? R(0.0) : infiltration_sub;
-    const R bottom = C.move_wetting_front_warp(go, fd, infil_arg, AET_sub, ending_volume_sub, dt, c, nodebuf);
+    const R bottom = C.move_wetting_front_warp(go, fd, infil_arg, AET_sub, ending_volume_sub, dt, c);
     if (go && !create) {
       percolation_sub = bottom;
       T.acc[LGAR_OUT_PERCOLATION] = T.acc[LGAR_OUT_PERCOLATION] + percolation_sub;
@@ -222,7 +222,7 @@ __device__ void substep(Tile<FM, R>& T, bool act, double precip_rate, double pet
       theta_1 = C.g(F_THETA, 0);
       theta_2 = R(C.soil[0].the);
     }
-    const R geff = geff_warpR(needG, theta_1, theta_2, C.soil[0], nint, nodebuf, c);
+    const R geff = geff_warpR<GM>(needG, theta_1, theta_2, C.soil[0], nint, nodebuf, c);
     if (needG && c.st == 0) {
       const SoilT<R>& s = C.soil[0];
       const R cur_theta = C.g(F_THETA, 0);
@@ -300,7 +300,7 @@ __device__ void substep(Tile<FM, R>& T, bool act, double precip_rate, double pet
           needG = (c.st == 0);
         }
       }
-      const R geff = geff_warpR(needG, theta_1, theta_2, C.soil[needG ? l : 0], nint, nodebuf, c);
+      const R geff = geff_warpR<GM>(needG, theta_1, theta_2, C.soil[needG ? l : 0], nint, nodebuf, c);
       if (needG && c.st == 0) {
         const SoilT<R>& s = C.soil[l];
         const R depth = C.g(F_DEPTH, i);
@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(NT, (FM == 16) ? 2 : ((FM == 12) ? 3 : 4)) lga
 #pragma unroll
       for (int k = 0; k < NOUT; k++) T.acc[k] = 0.0;
       const bool alive = valid && (T.ctx.st == 0);
-      for (int sc = 0; sc < S; sc++) substep(T, alive, x.x, x.y, K, nodebuf);
+      for (int sc = 0; sc < S; sc++) substep<FM, double, COUNT ? 2 : 0>(T, alive, x.x, x.y, K, nodebuf);
       if (alive && T.ctx.st != 0) T.crash_step = t;
       const bool ok = valid && (T.ctx.st == 0);
       T.acc[LGAR_OUT_ENDING_VOLUME] = T.col.ending_volume;

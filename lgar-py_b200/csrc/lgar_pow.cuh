@@ -41,27 +41,33 @@ struct PowExpEntry { double t, tail; };
 #ifdef __CUDACC__
 __device__ const PowLogEntry g_pow_log_table[LGAR_POW_N] = {LGAR_POW_LOG_TABLE};
 __device__ const PowExpEntry g_pow_exp_table[LGAR_POW_N] = {LGAR_POW_EXP_TABLE};
-// Per-CTA copies in shared memory (6 KB): the look-ups are data-dependent, so a warp touches up to 32
-// different rows; from shared memory that is a few wavefronts at ~25 cycles instead of 32 L1 tag look-ups
-// at global-load latency on the critical path of every pow.  Every kernel that evaluates pow_core on the
-// device calls pow_tables_to_shared() once before its first pow.
-// LGAR_POW_TABLES_GLOBAL (the reverse kernel's unit, whose shared memory is booked by the value + tape-id
-// arrays): only the 2 KB exp table is copied, the 4 KB log table stays in global memory (L1).
-#ifndef LGAR_POW_TABLES_GLOBAL
+// Table placement (measured on B200, tools/ + DESIGN.md): the look-ups are data-dependent (a warp touches up to
+// 32 different rows).  The 2 KB exp table is copied to shared memory by every kernel (pow_tables_to_shared(), once
+// per CTA, before its first pow); the 4 KB log table stays in global memory / L1: a shared-memory copy shortens a
+// lone warp's pow by ~3 % but costs 5 % THROUGHPUT at full occupancy (two 16-byte LDS per pow with random rows
+// serialise on bank conflicts), and throughput is what the ensemble runs are bound by.
+// LGAR_POW_LOG_SHARED / LGAR_POW_EXP_GLOBAL select the other placements (A/B builds).
+#ifdef LGAR_POW_LOG_SHARED
 __shared__ double2 s_pow_log_table[2 * LGAR_POW_N];
 #define LGAR_POW_LOG_ROW(i2) s_pow_log_table[i2]
 #else
 #define LGAR_POW_LOG_ROW(i2) __ldg(reinterpret_cast<const double2*>(g_pow_log_table) + (i2))
 #endif
+#ifndef LGAR_POW_EXP_GLOBAL
 __shared__ double2 s_pow_exp_table[LGAR_POW_N];
 #define LGAR_POW_EXP_ROW(j) s_pow_exp_table[j]
+#else
+#define LGAR_POW_EXP_ROW(j) __ldg(reinterpret_cast<const double2*>(g_pow_exp_table) + (j))
+#endif
 __device__ __forceinline__ void pow_tables_to_shared() {
-#ifndef LGAR_POW_TABLES_GLOBAL
+#ifdef LGAR_POW_LOG_SHARED
   for (int i = threadIdx.x; i < 2 * LGAR_POW_N; i += blockDim.x)
     s_pow_log_table[i] = reinterpret_cast<const double2*>(g_pow_log_table)[i];
 #endif
+#ifndef LGAR_POW_EXP_GLOBAL
   for (int i = threadIdx.x; i < LGAR_POW_N; i += blockDim.x)
     s_pow_exp_table[i] = reinterpret_cast<const double2*>(g_pow_exp_table)[i];
+#endif
   __syncthreads();
 }
 #endif
