@@ -47,8 +47,9 @@ def parse():
     ap.add_argument("--cpu-sample-columns", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--grad-columns", type=int, default=16384,
-                    help="columns of the shard used for the forward+gradient figure (0 = skip)")
+    ap.add_argument("--grad-columns", type=int, default=37888,
+                    help="columns of the shard used for the forward+gradient figure (0 = skip); the default is one "
+                         "32-column tile for each of the 148 SMs x 2 CTAs x 4 resident warps of the reverse kernel")
     return ap.parse_args()
 
 

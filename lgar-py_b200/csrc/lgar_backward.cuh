@@ -80,7 +80,8 @@ __host__ inline size_t backward_scratch_bytes(int S, int FM, int chunk, int slot
   return per * slots + 8192;
 }
 
-template <int FM>
+// GM = 0: trapezoid Geff only (closed-form branch compiled out of the taped sub-step); GM = 2: run-time switch
+template <int FM, int GM>
 __global__ void __launch_bounds__(NT) lgar_backward_kernel(const BParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sm_fields = reinterpret_cast<double*>(smem_raw);                       // [5*FM][NT]
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(NT) lgar_backward_kernel(const BParams P) {
           if (x.y > 0.0) precompute_psi_wp(Tv, p.wilting_point_psi);
 #pragma unroll
           for (int k = 0; k < NOUT; k++) Tv.acc[k] = Var(0.0);
-          substep<FM, Var, 2>(Tv, alive, x.x, x.y, K, nodebuf);
+          substep<FM, Var, GM>(Tv, alive, x.x, x.y, K, nodebuf);
           __syncwarp();
           if (tc.n > tc.cap) overflow = true;
           const int ne = min(tc.n, tc.cap);

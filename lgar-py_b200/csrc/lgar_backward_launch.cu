@@ -21,10 +21,10 @@ namespace lgar {
     }                                                                                     \
   } while (0)
 
-template <int FM>
+template <int FM, int GM>
 static int launch_backward(BParams& P, int S, int chunk, int slots, int arena_cap, int step_cap, int num_sms,
                            unsigned char* scratch, cudaStream_t st, char* err, size_t errlen) {
-  auto kern = lgar_backward_kernel<FM>;
+  auto kern = lgar_backward_kernel<FM, GM>;
   const size_t smem = (size_t)5 * FM * NT * sizeof(double) + (size_t)WARPS * NODEBUF * sizeof(double) +
                       (size_t)5 * FM * NT * sizeof(short) + (size_t)FM * NT;
   BW_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -63,7 +63,9 @@ int lgar_reverse_unit_launch(int FM, void* params, int S, int chunk, int slots, 
   using namespace lgar;
   BParams& P = *static_cast<BParams*>(params);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (FM == 8) return launch_backward<8>(P, S, chunk, slots, arena_cap, step_cap, num_sms, scratch, st, err, errlen);
-  if (FM == 12) return launch_backward<12>(P, S, chunk, slots, arena_cap, step_cap, num_sms, scratch, st, err, errlen);
-  return launch_backward<16>(P, S, chunk, slots, arena_cap, step_cap, num_sms, scratch, st, err, errlen);
+  if (FM == 8) return launch_backward<8, 2>(P, S, chunk, slots, arena_cap, step_cap, num_sms, scratch, st, err, errlen);
+  if (FM == 12) return launch_backward<12, 2>(P, S, chunk, slots, arena_cap, step_cap, num_sms, scratch, st, err, errlen);
+  // the default configuration gets a trapezoid-only instantiation (hot-path code size)
+  if (P.K.p.use_closed_form_G) return launch_backward<16, 2>(P, S, chunk, slots, arena_cap, step_cap, num_sms, scratch, st, err, errlen);
+  return launch_backward<16, 0>(P, S, chunk, slots, arena_cap, step_cap, num_sms, scratch, st, err, errlen);
 }
