@@ -140,7 +140,8 @@ typedef struct lgar_outputs {
   /* work counters, summed over columns and steps: 0 geff calls, 1 theta_from_h, 2 h_from_se,
    * 3 k_from_se, 4 se_from_h, 5 theta root-finder iterations, 6 column-mass iterations,
    * 7 sub-steps.  Used for the algorithmic FLOP count of the roofline.            */
-  unsigned long long* counters; /* [8]                                                          */
+  unsigned long long* counters; /* [16]: 0-7 work counters; 8-11 warp cycles in insert-water Geff, move
+                                   sweep, dry-depth Geff, calc_dzdt; 12 total warp cycles; 13-15 reserved   */
   /* diagnostics: SM cycles spent on each tile of 32 consecutive columns, summed over chunks     */
   unsigned long long* tile_cycles; /* [ceil(B/32)]                                              */
 } lgar_outputs;

@@ -128,7 +128,7 @@ class ForwardResult:
     fronts: Optional[torch.Tensor] = None          # [T,16,5,B]
     front_layer: Optional[torch.Tensor] = None     # [T,16,B]
     front_to_bottom: Optional[torch.Tensor] = None # [T,16,B]
-    counters: Optional[torch.Tensor] = None        # [8] int64
+    counters: Optional[torch.Tensor] = None        # [16] int64: 8 work counters + phase timers (lgar_b200.h)
     tile_cycles: Optional[torch.Tensor] = None     # [ceil(B/32)] int64 (diagnostics)
 
     def __getitem__(self, name) -> torch.Tensor:
@@ -180,7 +180,7 @@ def forward_raw(ens: ColumnEnsemble, alpha, n, ksat, outputs=("runoff", "percola
         o.fronts, o.front_layer = res.fronts.data_ptr(), res.front_layer.data_ptr()
         o.front_to_bottom = res.front_to_bottom.data_ptr()
     if counters or dump_fronts:
-        res.counters = torch.zeros(8, dtype=torch.int64, device=dev)
+        res.counters = torch.zeros(16, dtype=torch.int64, device=dev)
         o.counters = res.counters.data_ptr()
     if tile_cycles:
         res.tile_cycles = torch.zeros((B + 31) // 32, dtype=torch.int64, device=dev)

@@ -226,7 +226,7 @@ int lgar_forward(const lgar_problem* p, const lgar_outputs* out, void* workspace
   K.keep_ckpt = keep_checkpoints ? 1 : 0;
   K.iter_cap = p->iter_cap > 0 ? p->iter_cap : 1000000;
   CUDA_TRY(cudaMemsetAsync(w + c.off_done, 0, c.total - c.off_done, st));
-  if (out->counters) CUDA_TRY(cudaMemsetAsync(out->counters, 0, 8 * sizeof(unsigned long long), st));
+  if (out->counters) CUDA_TRY(cudaMemsetAsync(out->counters, 0, 16 * sizeof(unsigned long long), st));
   if (out->tile_cycles)
     CUDA_TRY(cudaMemsetAsync(out->tile_cycles, 0, (size_t)s.ntiles * sizeof(unsigned long long), st));
   // the kernels without work counters are trapezoid-only (closed-form branch compiled out of the hot path)
@@ -314,7 +314,7 @@ int lgar_forward_host(const lgar_problem* ph, const lgar_outputs* oh) {
 #define AL(field, count) if ((rc = db.alloc(oh->field, (count), &o.field))) return rc;
   AL(per_step, (size_t)__builtin_popcount(oh->per_step_mask) * T * B) AL(sums, (size_t)LGAR_NUM_OUTPUTS * B) AL(start_volume, B)
   AL(status, B) AL(crash_step, B) AL(num_fronts, T * B) AL(fronts, T * LGAR_MAX_FRONTS * 5 * B)
-  AL(front_layer, T * LGAR_MAX_FRONTS * B) AL(front_to_bottom, T * LGAR_MAX_FRONTS * B) AL(counters, 8)
+  AL(front_layer, T * LGAR_MAX_FRONTS * B) AL(front_to_bottom, T * LGAR_MAX_FRONTS * B) AL(counters, 16)
   AL(tile_cycles, (size_t)s.ntiles)
 #undef AL
   const size_t wsb = lgar_workspace_bytes(&p, 0);
@@ -328,7 +328,7 @@ int lgar_forward_host(const lgar_problem* ph, const lgar_outputs* oh) {
   if (oh->field) CUDA_TRY(cudaMemcpy(oh->field, o.field, (count) * sizeof(*oh->field), cudaMemcpyDeviceToHost));
   DOWN(per_step, (size_t)__builtin_popcount(oh->per_step_mask) * T * B) DOWN(sums, (size_t)LGAR_NUM_OUTPUTS * B) DOWN(start_volume, B)
   DOWN(status, B) DOWN(crash_step, B) DOWN(num_fronts, T * B) DOWN(fronts, T * LGAR_MAX_FRONTS * 5 * B)
-  DOWN(front_layer, T * LGAR_MAX_FRONTS * B) DOWN(front_to_bottom, T * LGAR_MAX_FRONTS * B) DOWN(counters, 8)
+  DOWN(front_layer, T * LGAR_MAX_FRONTS * B) DOWN(front_to_bottom, T * LGAR_MAX_FRONTS * B) DOWN(counters, 16)
   DOWN(tile_cycles, (size_t)s.ntiles)
 #undef DOWN
   return 0;

@@ -49,6 +49,8 @@ struct Ctx {  // per-thread execution context
   int st;               // lgar_status, first error wins
   unsigned cnt[8];      // work counters
   long long iter_cap;
+  unsigned long long ph[4];  // phase timers (clock64 deltas; counting kernels only): 0 insert-water Geff, 1 move sweep +
+                             // merge/cross/fix/update_psi, 2 dry-depth Geff + surficial front, 3 calc_dzdt (Geff per front)
 };
 
 __device__ __forceinline__ void raise(Ctx& c, int code) {
@@ -343,6 +345,26 @@ __device__ __forceinline__ double tmin(double a, double b) {
 //            nodes j, j+32, j+64, ...
 //   stage C (requesting lane): geff = sum_i (K_{i-1} + K_i) * (dh / 2) in the reference's order.
 // ------------------------------------------------------------------------------------
+// Trapezoid terms of one Geff request, evaluated by all lanes: nodebuf[i] := (K_{i-1} + K_i) * (dh / 2) for
+// i = 1..nint (the same two operations as the reference's loop body), staged through registers so that the buffer
+// is rewritten in place.  The requesting lane then only carries the sequential `geff = geff + term_i` chain
+// (one DADD per node instead of DADD + DMUL + DADD at 1 active lane of 32).  Warp-convergent.
+__device__ __forceinline__ void geff_terms_inplace(double* nodebuf, int nint, double half) {
+  const int lane = threadIdx.x & 31;
+  double t[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int i = lane + 1 + 32 * r;
+    t[r] = (i <= nint) ? (nodebuf[i - 1] + nodebuf[i]) * half : 0.0;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int i = lane + 1 + 32 * r;
+    if (i <= nint) nodebuf[i] = t[r];
+  }
+  __syncwarp();
+}
 struct GeffRet {
   double v;
   int st;
@@ -425,17 +447,12 @@ __device__ __noinline__ GeffRet geff_warp_core(bool need, double theta_1, double
       st_any = __shfl_sync(0xffffffffu, cc_st, b);
     }
     __syncwarp();
+    geff_terms_inplace(nodebuf, nint, qdh / 2.0);
     if (lane == src) {
       if (st_any) raise(c, st_any);
-      const double half = qdh / 2.0;
       double geff = 0.0;
-      double k1 = nodebuf[0];
 #pragma unroll 8
-      for (int i = 1; i <= nint; i++) {
-        double k2 = nodebuf[i];
-        geff = geff + ((k1 + k2) * half);
-        k1 = k2;
-      }
+      for (int i = 1; i <= nint; i++) geff = geff + nodebuf[i];
       result = fabs(geff / s.ksat);
     }
     __syncwarp();
@@ -856,17 +873,12 @@ __device__ Var geff_warpR(bool need, const Var& theta_1, const Var& theta_2, con
     S = warp_sum(S); Ahi = warp_sum(Ahi); Ahf = warp_sum(Ahf); Ca = warp_sum(Ca); Cn = warp_sum(Cn);
     Cm = warp_sum(Cm); Csei = warp_sum(Csei);
     __syncwarp();
+    geff_terms_inplace(nodebuf, nint, qdh / 2.0);
     if (lane == src) {
       if (st_any) raise(ca, st_any);
-      const double half = qdh / 2.0;
       double geff = 0.0;
-      double k1 = nodebuf[0];
 #pragma unroll 8
-      for (int i = 1; i <= nint; i++) {
-        const double k2 = nodebuf[i];
-        geff = geff + ((k1 + k2) * half);
-        k1 = k2;
-      }
+      for (int i = 1; i <= nint; i++) geff = geff + nodebuf[i];
       const double value = fabs(geff / s.ksat);
       const double G = qdh * S;
       const double sg = (G / q.ksat > 0.0) ? 1.0 : ((G / q.ksat < 0.0) ? -1.0 : 0.0);

@@ -142,6 +142,8 @@ __device__ void substep(Tile<FM, R>& T, bool act, double precip_rate, double pet
   const bool brA = act && create && !saturated;             // create a surficial front
   const bool brB = act && !create && (ponded_depth_sub > 0.0);  // insert water
 
+  const bool timed = (GM == 2) && K.o.counters != nullptr;  // counting instantiations only
+  long long tph = timed ? clock64() : 0;
   // ---- phase 1: Layer.insert_water (Layer.py:1418-1536) for branch-B lanes
   {
     int lfp = 0, nx_fd = 0;
@@ -202,6 +204,7 @@ __device__ void substep(Tile<FM, R>& T, bool act, double precip_rate, double pet
     }
   }
 
+  if (timed) { const long long t = clock64(); c.ph[0] += (unsigned long long)(t - tph); tph = t; }
   // ---- phase 2: move the fronts (branch A moves without adding water; every non-create lane moves
   //      with its infiltration).  models/dpLGAR.py:206-212 and :249-266
   {
@@ -214,6 +217,7 @@ __device__ void substep(Tile<FM, R>& T, bool act, double precip_rate, double pet
     }  // branch A drops the bottom flux (Q7)
   }
 
+  if (timed) { const long long t = clock64(); c.ph[1] += (unsigned long long)(t - tph); tph = t; }
   // ---- phase 3: calc_dry_depth (Layer.py:1309-1334) + create_surficial_front (:1336-1416)
   {
     const bool needG = brA && c.st == 0;
@@ -269,6 +273,7 @@ __device__ void substep(Tile<FM, R>& T, bool act, double precip_rate, double pet
     T.acc[LGAR_OUT_RUNOFF] = T.acc[LGAR_OUT_RUNOFF] + runoff_sub;
   }
 
+  if (timed) { const long long t = clock64(); c.ph[2] += (unsigned long long)(t - tph); tph = t; }
   // ---- phase 4: Layer.calc_dzdt (Layer.py:1176-1252), one cooperative Geff per moving front
   {
     const bool go = act && c.st == 0;
@@ -319,6 +324,7 @@ __device__ void substep(Tile<FM, R>& T, bool act, double precip_rate, double pet
     }
   }
 
+  if (timed) { const long long t = clock64(); c.ph[3] += (unsigned long long)(t - tph); tph = t; }
   if (act) {
     ending_volume_sub = C.mass_balance();
     C.previous_precip = precip_sub;
@@ -468,6 +474,8 @@ __global__ void __launch_bounds__(NT, (FM == 16) ? 2 : ((FM == 12) ? 3 : 4)) lga
     }
 #pragma unroll
     for (int k = 0; k < 8; k++) T.ctx.cnt[k] = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) T.ctx.ph[k] = 0;
     const long long clk0 = clock64();
     load_params(K, bb, T);
     const int slot_in = K.keep_ckpt ? chunk : 0;
@@ -543,6 +551,11 @@ __global__ void __launch_bounds__(NT, (FM == 16) ? 2 : ((FM == 12) ? 3 : 4)) lga
 #pragma unroll
       for (int k = 0; k < 8; k++)
         if (T.ctx.cnt[k]) atomicAdd(K.o.counters + k, (unsigned long long)T.ctx.cnt[k]);
+      if (lane == 0) {  // phase timers of this warp (entries 8..11) and its total chunk time (12)
+#pragma unroll
+        for (int k = 0; k < 4; k++) atomicAdd(K.o.counters + 8 + k, T.ctx.ph[k]);
+        atomicAdd(K.o.counters + 12, (unsigned long long)(clock64() - clk0));
+      }
     }
     __threadfence();
     __syncwarp();

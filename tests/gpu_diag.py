@@ -27,11 +27,18 @@ for B, T in shapes:
         e0.record(); forward_raw(ens, we.alpha, we.n, we.ksat, outputs=("runoff", "AET"), workspace=ws); e1.record()
         torch.cuda.synchronize(); times.append(e0.elapsed_time(e1))
     kms = min(times)
+    cn = res.counters.cpu().numpy().astype(np.float64)
+    if cn.shape[0] >= 13 and cn[12] > 0:
+        names = ("insert-water Geff", "move sweep + merge/cross/fix/update_psi", "dry-depth Geff + surficial front", "calc_dzdt Geff")
+        print("  warp-cycle shares (counting pass): " + ", ".join(f"{nm} {100 * cn[8 + i] / cn[12]:.1f} %" for i, nm in enumerate(names))
+              + f", rest {100 * (1 - cn[8:12].sum() / cn[12]):.1f} %", flush=True)
     st = res.status.cpu().numpy(); cr = res.crash_step.cpu().numpy()
     alive = int(np.where(st == 0, T, np.maximum(cr, 0)).sum())
     if os.environ.get("LGAR_DIAG_SAVE"):
         os.makedirs("gpurun_out", exist_ok=True)
         np.savez_compressed(f"gpurun_out/diag_{B}x{T}{os.environ.get('LGAR_DIAG_TAG', '')}.npz", sums=res.sums.cpu().numpy(), status=st, crash=cr)
     tc = res.tile_cycles.cpu().numpy(); top = np.argsort(-tc)[:4]
+    print(f"  tile busy time: sum {tc.sum() / 1.965e9:.1f} s = {tc.sum() / 1.965e9 / 1184:.3f} s per resident warp (1184), "
+          f"max {tc.max() / 1.965e9:.3f} s, mean {tc.mean() / 1.965e9:.4f} s, p99 {np.percentile(tc, 99) / 1.965e9:.3f} s", flush=True)
     print("  slowest tiles:", [(int(i), round(float(tc[i]) / 1.9e9, 2)) for i in top], "median tile s", round(float(np.median(tc)) / 1.9e9, 3), flush=True)
     print(f"B={B} T={T}: first {dt:.3f}s, best of {len(times)} passes {kms:.1f} ms (all: {[round(x) for x in times]}) -> {alive/kms*1e3:.4g} col-steps/s  alive col-steps={alive}  status hist={np.bincount(st, minlength=9).tolist()} counters={res.counters.cpu().numpy().tolist()}", flush=True)
