@@ -138,7 +138,11 @@ class DifferentiableLGAR:
     OUTPUTS = ("runoff", "percolation", "AET", "infiltration", "ending_volume", "ponded_water", "giuh_runoff", "precip",
                "PET", "discharge")
 
-    def __init__(self, cfg, model=None, x=None, y=None, device="cuda", group=None) -> None:
+    def __init__(self, cfg, model=None, x=None, y=None, device="cuda", group=None, on_column_error="raise") -> None:
+        """on_column_error: "raise" (reference semantics: an exception inside model(x) aborts the run) or "mask"
+        (sites whose column failed in this epoch are left out of the loss; useful with many sites per rank)."""
+        assert on_column_error in ("raise", "mask")
+        self.on_column_error = on_column_error
         self.cfg = cfg
         torch.manual_seed(0)
         torch.set_default_dtype(torch.float64)
@@ -192,18 +196,26 @@ class DifferentiableLGAR:
         self.optimizer.zero_grad()
         out = self.model.forward_record(self.x if self.x.shape[0] > 1 else self.x[0], outputs=self.OUTPUTS)
         st = out.get("status")
+        keep = None
         if st is not None and bool((st != 0).any()):  # the reference raises out of model(x)
             from ._capi import STATUS_NAMES
-            bad = int(st.reshape(-1)[(st.reshape(-1) != 0).nonzero()[0, 0]])
-            step = int(out["crash_step"].reshape(-1)[(st.reshape(-1) != 0).nonzero()[0, 0]])
-            raise RuntimeError(f"LGAR column status {STATUS_NAMES[bad]} at forcing step {step} (the reference raises here)")
+            first = (st.reshape(-1) != 0).nonzero()[0, 0]
+            bad, step = int(st.reshape(-1)[first]), int(out["crash_step"].reshape(-1)[first])
+            msg = f"LGAR column status {STATUS_NAMES[bad]} at forcing step {step} (the reference raises here)"
+            if self.on_column_error == "raise":
+                raise RuntimeError(msg)
+            keep = (st.reshape(-1) == 0)
+            log.warning(f"{int((~keep).sum())} of {keep.numel()} sites left out of this epoch: {msg}")
         self._report_mass(out)
         y_hat = out["runoff"]
         if y_hat.dim() == 1:
             y_hat = y_hat[:, None]
         y_hat = y_hat.transpose(0, 1)                           # [sites, T]
+        y_t = self.y.to(y_hat.device)
+        if keep is not None:
+            y_hat, y_t = y_hat[keep], y_t[keep]
         self.y_hat = y_hat[:, self.warmup:]
-        self.y_t = self.y[:, self.warmup:].to(y_hat.device)
+        self.y_t = y_t[:, self.warmup:]
         self.validate()
 
     def validate(self) -> None:
