@@ -93,7 +93,8 @@ typedef struct lgar_problem {
   int32_t num_sites;       /* number of forcing series                                          */
   int32_t nint;            /* Geff trapezoid intervals       cfg.constants.nint (120)           */
   int32_t num_giuh;        /* <= LGAR_MAX_GIUH               cfg.data.giuh_ordinates            */
-  int32_t max_fronts;      /* 8, 12 or 16 (0 = 16): front-list capacity per column              */
+  int32_t max_fronts;      /* 8, 12, 16 or 32 (0 = 16): front-list capacity per column; 32 is
+                              forward-only (one CTA per SM): the fallback for LGAR_ST_FRONT_OVERFLOW  */
   int32_t chunk_steps;     /* forcing steps per scheduling/checkpoint chunk (0 = default 64)    */
   int32_t resume;          /* 0: start from set_internal_states() (models/dpLGAR.py:97-147);
                               1: continue from the column state the previous lgar_forward left in

@@ -130,6 +130,7 @@ class ForwardResult:
     front_to_bottom: Optional[torch.Tensor] = None # [T,16,B]
     counters: Optional[torch.Tensor] = None        # [16] int64: 8 work counters + phase timers (lgar_b200.h)
     tile_cycles: Optional[torch.Tensor] = None     # [ceil(B/32)] int64 (diagnostics)
+    overflow_reruns: int = 0                       # columns rerun with the 32-front kernel (overflow_fallback)
 
     def __getitem__(self, name) -> torch.Tensor:
         k = OUT_NAMES.index(name)
@@ -144,10 +145,42 @@ def _param(x, ens: ColumnEnsemble):
     return t.to(ens.device, non_blocking=True).contiguous()
 
 
+FRONT_OVERFLOW = 6  # lgar_status: more than max_fronts wetting fronts (capacity of the library, not a reference state)
+
+
+def _rerun_overflowed(ens: ColumnEnsemble, alpha, n, ksat, res: "ForwardResult", outputs, per_step) -> int:
+    """The reference's front lists are unbounded; the production kernels hold 16 fronts per column in shared memory.
+    The (rare: ~0.07 % of the bench ensemble over a year) columns that overflow are run again with the 32-front
+    instantiation (one CTA per SM) and their results scattered into `res`.  Returns the number of columns rerun."""
+    idx = (res.status == FRONT_OVERFLOW).nonzero().flatten()
+    if idx.numel() == 0 or int(ens.max_fronts) >= 32 or ens.resume:
+        return 0
+    sub = ColumnEnsemble(
+        theta_r=ens.theta_r[:, idx], theta_e=ens.theta_e[:, idx], thickness=ens.thickness[:, idx], forcing=ens.forcing,
+        site_index=(ens.site_index[idx] if ens.site_index is not None else None), initial_psi=ens.initial_psi[idx],
+        ponded_depth_max=ens.ponded_depth_max[idx], subcycle_length_h=ens.subcycle_length_h,
+        num_subcycles=ens.num_subcycles, nint=ens.nint, wilting_point_psi=ens.wilting_point_psi,
+        frozen_factor=ens.frozen_factor, use_closed_form_G=ens.use_closed_form_G, giuh_ordinates=ens.giuh_ordinates,
+        max_fronts=32, chunk_steps=ens.chunk_steps, iter_cap=ens.iter_cap, device=ens.device)
+    r2, _ = forward_raw(sub, alpha[:, idx].contiguous(), n[:, idx].contiguous(), ksat[:, idx].contiguous(), outputs=outputs,
+                        per_step=per_step, num_fronts=res.num_fronts is not None, overflow_fallback=False)
+    if res.per_step is not None:
+        res.per_step[:, :, idx] = r2.per_step
+    res.sums[:, idx] = r2.sums
+    res.start_volume[idx] = r2.start_volume
+    res.status[idx] = r2.status
+    res.crash_step[idx] = r2.crash_step
+    if res.num_fronts is not None:
+        res.num_fronts[:, idx] = r2.num_fronts
+    return int(idx.numel())
+
+
 def forward_raw(ens: ColumnEnsemble, alpha, n, ksat, outputs=("runoff", "percolation"), per_step=True,
                 num_fronts=False, dump_fronts=False, counters=False, tile_cycles=False, keep_checkpoints=False,
-                workspace: Optional[torch.Tensor] = None) -> tuple[ForwardResult, torch.Tensor]:
-    """One persistent launch over all columns and all forcing steps (no autograd)."""
+                workspace: Optional[torch.Tensor] = None, overflow_fallback=False) -> tuple[ForwardResult, torch.Tensor]:
+    """One persistent launch over all columns and all forcing steps (no autograd).
+    overflow_fallback: rerun the columns that overflowed the front list with the 32-front kernel (synchronises:
+    the status array is inspected on the host)."""
     L_ = _capi.lib()
     dev = ens.device
     alpha, n, ksat = _param(alpha, ens), _param(n, ens), _param(ksat, ens)
@@ -191,6 +224,8 @@ def forward_raw(ens: ColumnEnsemble, alpha, n, ksat, outputs=("runoff", "percola
                              1 if keep_checkpoints else 0, C.c_void_p(stream))
     _capi.check(rc, "lgar_forward")
     res._keep = (alpha, n, ksat, ens)  # keep inputs alive until the stream has consumed them
+    if overflow_fallback and not keep_checkpoints and not dump_fronts:
+        res.overflow_reruns = _rerun_overflowed(ens, alpha, n, ksat, res, outputs, per_step)
     return res, workspace
 
 

@@ -46,7 +46,8 @@ int shape_of(const lgar_problem* p, Shape& s) {
   s.T = p->num_steps;
   s.S = p->num_subcycles;
   s.FM = p->max_fronts == 0 ? 16 : p->max_fronts;
-  if (s.FM != 8 && s.FM != 12 && s.FM != 16) return fail(LGAR_E_INVALID, "max_fronts must be 8, 12 or 16");
+  if (s.FM != 8 && s.FM != 12 && s.FM != 16 && s.FM != 32)
+    return fail(LGAR_E_INVALID, "max_fronts must be 8, 12, 16 or 32");
   s.chunk = p->chunk_steps > 0 ? p->chunk_steps : 64;
   s.nchunks = (s.T + s.chunk - 1) / s.chunk;
   s.ntiles = s.Bp / 32;
@@ -200,6 +201,7 @@ int lgar_forward(const lgar_problem* p, const lgar_outputs* out, void* workspace
     return fail(LGAR_E_INVALID, "a required problem array is NULL");
   if (p->num_sites < 1) return fail(LGAR_E_INVALID, "num_sites < 1");
   if (p->resume && keep_checkpoints) return fail(LGAR_E_INVALID, "resume is not available with keep_checkpoints");
+  if (s.FM == 32 && keep_checkpoints) return fail(LGAR_E_INVALID, "max_fronts = 32 is forward-only (no checkpoints)");
   int dev = -1;
   if (cudaGetDevice(&dev) != cudaSuccess || dev != g_dev_checked) {
     rc = lgar_device_check();
@@ -239,6 +241,7 @@ int lgar_forward(const lgar_problem* p, const lgar_outputs* out, void* workspace
   if (dump) rc = launch_forward<16, true, true>(K, st);
   else if (s.FM == 8) { LGAR_DISPATCH(8) }
   else if (s.FM == 12) { LGAR_DISPATCH(12) }
+  else if (s.FM == 32) rc = launch_forward<32, true, false>(K, st);  // large-capacity fallback (1 CTA per SM)
   else { LGAR_DISPATCH(16) }
 #undef LGAR_DISPATCH
   return rc;
@@ -252,6 +255,7 @@ int lgar_backward(const lgar_problem* p, const double* grad_per_step, uint32_t g
   int rc = shape_of(p, s);
   if (rc) return rc;
   if (!grad_alpha || !grad_n || !grad_ksat) return fail(LGAR_E_INVALID, "gradient output array is NULL");
+  if (s.FM == 32) return fail(LGAR_E_INVALID, "max_fronts = 32 is forward-only");
   int dev = -1;
   if (cudaGetDevice(&dev) != cudaSuccess || dev != g_dev_checked) {
     rc = lgar_device_check();

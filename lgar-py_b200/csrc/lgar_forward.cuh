@@ -425,10 +425,10 @@ __device__ void load_params(const KParams& K, int b, Tile<FM, R>& T) {
   C.pdm = __ldg(p.ponded_depth_max + b);
 }
 
-// resident CTAs per SM are bounded by the shared-memory front lists: 2 (FM = 16), 3 (FM = 12), 4 (FM = 8);
-// the register cap follows from that
+// resident CTAs per SM are bounded by the shared-memory front lists: 1 (FM = 32, the fallback for the rare columns
+// that overflow 16 fronts), 2 (FM = 16), 3 (FM = 12), 4 (FM = 8); the register cap follows from that
 template <int FM, bool COUNT, bool DUMP>
-__global__ void __launch_bounds__(NT, (FM == 16) ? 2 : ((FM == 12) ? 3 : 4)) lgar_forward_kernel(const KParams K) {
+__global__ void __launch_bounds__(NT, (FM == 32) ? 1 : ((FM == 16) ? 2 : ((FM == 12) ? 3 : 4))) lgar_forward_kernel(const KParams K) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sm_fields = reinterpret_cast<double*>(smem_raw);                       // [5*FM][NT]
   double* sm_nodes = sm_fields + 5 * FM * NT;                                    // [WARPS][NODEBUF]

@@ -139,3 +139,23 @@ def test_ragged_shapes(B, T):
     a = part["ending_volume"].cpu().numpy()[:, ok]
     b = ref["ending_volume"].cpu().numpy()[:T, cols][:, ok]
     np.testing.assert_array_equal(a, b)
+
+
+def test_front_overflow_fallback():
+    """Columns that overflow the front list are rerun with the 32-front instantiation: with an 8-front base kernel
+    plus the fallback every column must give the bits of the 16-front kernel."""
+    from lgar_b200 import workloads, forward_raw
+    B, T = 16384, 640
+    we = workloads.synthetic_sites_ensemble(B=B, T=T, sites=16, rank=0)
+    ref, _, _ = _run(we, outputs=OUTS)                                   # 16 fronts
+    small, _, _ = _run(we, outputs=OUTS, max_fronts=8)                   # 8 fronts, no fallback
+    n_over = int((small.status == 6).sum())
+    assert n_over > 0, "the case must contain overflowing columns"
+    ens8 = _ens(we, max_fronts=8)
+    fb, _ = forward_raw(ens8, we.alpha, we.n, we.ksat, outputs=OUTS, overflow_fallback=True)
+    torch.cuda.synchronize()
+    assert fb.overflow_reruns == n_over
+    assert torch.equal(fb.status, ref.status) and torch.equal(fb.crash_step, ref.crash_step)
+    ok = ref.status == 0
+    assert torch.equal(fb.sums[:, ok].contiguous().view(torch.int64), ref.sums[:, ok].contiguous().view(torch.int64))
+    assert torch.equal(fb["runoff"][:, ok].contiguous().view(torch.int64), ref["runoff"][:, ok].contiguous().view(torch.int64))
