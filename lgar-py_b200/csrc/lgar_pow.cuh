@@ -240,8 +240,12 @@ LGAR_HD void pow_core_v(const double (&x)[N], const double (&y)[N], double (&res
 LGAR_HD double pow_inverse_root(double u, double d, double se, double resid, double log_u, double m, double inv_m) {
   const double eps = pow_fma(se, d, -1.0);
   const double tau = pow_fma(inv_m, m, -1.0);
-  const double c = (eps + resid / d) * inv_m - tau * log_u;
+  const double c = (eps + resid * se) * inv_m - tau * log_u;  // resid / d = resid * se (1 + O(2^-53)), resid is ~2^-53 d
+#ifdef __CUDA_ARCH__
+  const double w_hi = __drcp_rn(u);  // IEEE reciprocal: cheaper than the general division
+#else
   const double w_hi = 1.0 / u;
+#endif
   const double w_lo = -pow_fma(w_hi, u, -1.0) * w_hi;
   return w_hi + (w_lo + w_hi * c);
 }
