@@ -56,9 +56,10 @@ def parse():
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
 
-    def __init__(self, index=0):
+    def __init__(self, index=0, interval=0.2):
         super().__init__(daemon=True)
         self.index = index
+        self.interval = interval
         self.rows = []
         self.stop_flag = False
 
@@ -73,7 +74,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(self.interval)
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
@@ -185,9 +186,9 @@ def main():
     for _ in range(max(args.warmup - 1, 0)):
         one_pass()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    # every rank samples its own GPU (rank 0's summary goes into `clocks`; the others sample once per second)
+    sampler = ClockSampler(local, interval=0.2 if rank == 0 else 1.0)
+    sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     ev[0].record()
     for i in range(args.steps):
@@ -263,6 +264,18 @@ def main():
     else:
         e2e_ms_all, alive_all, flop_all = float(stats[3]), float(alive_steps), flop_per_launch
         fg_ms_all, fg_alive_all = float(stats[4]), float(stats[5])
+    # per-rank step time and SM clock (diagnosis of weak-scaling losses: which rank / GPU was the slow one)
+    my_clk = sampler.summary()
+    per_rank = torch.tensor([float(stats[0]) / args.steps, float(my_clk["sm_mhz"] or 0.0),
+                             1.0 if my_clk["reasons"] else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        gathered = [torch.zeros_like(per_rank) for _ in range(world)]
+        dist.all_gather(gathered, per_rank)
+    else:
+        gathered = [per_rank]
+    per_rank_ms = [float(g[0]) for g in gathered]
+    per_rank_mhz = [float(g[1]) for g in gathered]
+    per_rank_throttled = [bool(g[2] > 0) for g in gathered]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -290,7 +303,8 @@ def main():
                    "alive_column_steps_per_gpu": alive_steps, "max_fronts": args.max_fronts, "chunk_steps": args.chunk,
                    "l2": "working set (per-step outputs 2 x T x B x 8 B = %.1f GB) exceeds L2; no flush needed" % (len(outs) * T * B * 8 / 1e9)},
         "gpu_launches": args.steps,
-        "clocks": sampler.summary(),
+        "clocks": my_clk,
+        "per_rank": {"ms_per_step": per_rank_ms, "sm_mhz": per_rank_mhz, "throttle_reason_seen": per_rank_throttled},
         "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
                      "peak_source": "in-run DFMA probe (lgar_measure_fp64_flops); MEASURED_PEAKS.json has no FP64 entry",
