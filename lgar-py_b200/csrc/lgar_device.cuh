@@ -86,7 +86,7 @@ __device__ __noinline__ double2 pow_log_f64(double a, double b) {
 }
 // two INDEPENDENT pows issued interleaved from one basic block (ILP: pow is one long dependent chain)
 __device__ __noinline__ double2 pow_x2(double x0, double y0, double x1, double y1) {
-#ifdef LGAR_POW_X2_VECTOR
+#ifdef LGAR_POW_X2_VECTOR  // A/B: source-interleaved pair (ptxas serialises it again; measured 0.4 % slower)
   const double xv[2] = {x0, x1}, yv[2] = {y0, y1};
   double r[2];
   bool ok[2];
@@ -308,9 +308,7 @@ __device__ __noinline__ double advance_rounded_pos(double x, double s, long long
     const double lim = (s > 0.0) ? __hiloint2double((e1 + 1) << 20, 0) : __hiloint2double(e1 << 20, 0);
     const double room = (s > 0.0) ? (lim - t) : (t - lim);
     // common case: all remaining steps fit ((k + 1) |c| <= room, tested conservatively) -- no division
-#ifndef LGAR_ADV_OLD
     if ((double)(k + 1) * fabs(c) * (1.0 + 0x1p-40) <= room) return fma((double)k, c, t);
-#endif
     long long n = (long long)floor(room / fabs(c)) - 1;
     if (n > k) n = k;
     if (n < 0) n = 0;
