@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "liblgar_b200.so")
 SOURCES = ["lgar_capi.cu", "lgar_backward_launch.cu"]
-HEADERS = ["lgar_device.cuh", "lgar_forward.cuh", "lgar_backward.cuh", "lgar_pow.cuh", "lgar_pow_tables.h", "lgar_var.cuh",
+HEADERS = ["lgar_device.cuh", "lgar_forward.cuh", "lgar_backward.cuh", "lgar_pow.cuh", "lgar_pow_tables.h", "lgar_var.cuh", "lgar_rounded.cuh",
            "../../include/lgar_b200.h"]
 
 NVCC_FLAGS = [

@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 #include "../../include/lgar_b200.h"
 #include "lgar_pow.cuh"
+#include "lgar_rounded.cuh"  // advance_rounded(): exact result of k rounded additions (host-testable)
 #include "lgar_var.cuh"
 #include <type_traits>
 
@@ -275,54 +276,6 @@ __device__ __forceinline__ double2 h_from_se_x2(double se0, double se1, const So
   if (bad) raise(c, bad);
   if (isnan(r.x) || isnan(r.y)) raise(c, LGAR_ST_NAN);
   return r;
-}
-
-// ------------------------------------------------------------------------------------
-// Exact result of k successive ROUNDED additions x = fl(x + s) (s may be negative), in
-// O(number of binades crossed) instead of O(k).  Inside one binade every x is a multiple of
-// ulp, so fl(x + s) - x is the same representable increment c for every step unless the
-// discarded part of s is exactly half an ulp (tie -> round-to-even alternates; those steps are
-// taken one by one).  Used by the root finder to jump along a monotone run of psi steps while
-// visiting exactly the psi values the reference's `psi = psi +/- 0.1*factor` loop visits.
-// ------------------------------------------------------------------------------------
-__device__ __forceinline__ int f64_exponent(double x) { return (__double2hiint(x) >> 20) & 0x7ff; }
-__device__ __noinline__ double advance_rounded_pos(double x, double s, long long k) {
-  while (k > 0) {
-    const double t = x + s;
-    k--;
-    if (k == 0 || !(t > 0.0)) return t;  // callers reject non-positive results
-    const int e0 = f64_exponent(x), e1 = f64_exponent(t);
-    const double c = t - x;    // exact (|s| << |x| in every caller)
-    const double err = s - c;  // exact rounding residual of this step
-    if (e0 != e1 || e1 <= 53 || e1 >= 0x7fe || !(t > 0.0)) {
-      x = t;
-      continue;
-    }
-    const double ulp = __hiloint2double((e1 - 52) << 20, 0);
-    if (fabs(err) * 2.0 == ulp || c == 0.0) {
-      if (c == 0.0) return t;  // x + s == x from here on
-      x = t;
-      continue;
-    }
-    // steps that stay strictly inside the binade of t with the constant increment c
-    const double lim = (s > 0.0) ? __hiloint2double((e1 + 1) << 20, 0) : __hiloint2double(e1 << 20, 0);
-    const double room = (s > 0.0) ? (lim - t) : (t - lim);
-    // common case: all remaining steps fit ((k + 1) |c| <= room, tested conservatively) -- no division
-    if ((double)(k + 1) * fabs(c) * (1.0 + 0x1p-40) <= room) return fma((double)k, c, t);
-    long long n = (long long)floor(room / fabs(c)) - 1;
-    if (n > k) n = k;
-    if (n < 0) n = 0;
-    x = fma((double)n, c, t);  // exact: the result is a multiple of ulp inside the binade
-    k -= n;
-  }
-  return x;
-}
-
-// round-to-nearest-even is symmetric under negation, so negative x mirror the positive case
-__device__ __forceinline__ double advance_rounded(double x, double s, long long k) {
-  const bool neg = x < 0.0;
-  const double r = advance_rounded_pos(neg ? -x : x, neg ? -s : s, k);
-  return neg ? -r : r;
 }
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
