@@ -158,12 +158,18 @@ const char* lgar_last_error_string(void);
 size_t lgar_workspace_bytes(const lgar_problem* p, int with_grad);
 
 /* Forward: advance all B columns through all T forcing steps in ONE persistent launch.
+ * Replaces the per-row calls `runoff, percolation = self.model(x)` of the reference's training loop
+ * (dpLGAR/agents/DifferentiableLGAR.py:117-125 -> dpLGAR.forward, dpLGAR/models/dpLGAR.py:154-299) together with
+ * set_internal_states (models/dpLGAR.py:97-147) and the accumulator resets of MassBalance.change_mass
+ * (models/physics/MassBalance.py:31-53).
  * If `workspace_dev` was sized with with_grad != 0, state checkpoints for lgar_backward are
  * stored in it (pass keep_checkpoints != 0).                                                   */
 int lgar_forward(const lgar_problem* p, const lgar_outputs* out, void* workspace_dev,
                  size_t workspace_bytes, int keep_checkpoints, void* stream);
 
-/* Reverse mode.  grad_per_step[popcount(grad_mask)][T][B] (same compact layout) and/or
+/* Reverse mode: replaces `loss.backward()` w.r.t. model.alpha / n / ksat (dpLGAR/agents/DifferentiableLGAR.py:163)
+ * with the reference's autograd semantics (straight-through root finders).
+ * grad_per_step[popcount(grad_mask)][T][B] (same compact layout) and/or
  * grad_sums[NOUT][B] are dL/d(output); writes dL/d(alpha,n,ksat) as [L][B] arrays.
  * Must follow an lgar_forward with keep_checkpoints on the same workspace and problem.         */
 int lgar_backward(const lgar_problem* p, const double* grad_per_step, uint32_t grad_mask,
