@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define LGAR_ABI_VERSION 1
+#define LGAR_ABI_VERSION 2
 #define LGAR_MAX_LAYERS 4      /* soil layers per column (all reference configs use 3)            */
 #define LGAR_MAX_FRONTS 16     /* capacity of the wetting-front list of one column                */
 #define LGAR_MAX_GIUH 8        /* GIUH ordinates (reference: 5, data/config/Phillipsburg.yaml)    */
@@ -102,6 +102,14 @@ typedef struct lgar_problem {
                               caller advance one forcing row per call like dpLGAR.forward(x)         */
   int32_t use_closed_form_G; /* cfg.data.use_closed_form_G: 0 = trapezoid Geff (green_ampt.py:45-84),
                               1 = Brooks-Corey closed form (green_ampt.py:85-98); was reserved (0) before   */
+  int32_t step_begin;      /* window [step_begin, step_end) of the forcing record advanced by this call   */
+  int32_t step_end;        /* (0, 0 = the whole record).  num_steps stays the length of the record: it
+                              fixes the layout of `forcing` and of the per-step outputs, and step indices
+                              (crash_step, rows of per_step) stay absolute.  A window that does not start
+                              at row 0 needs resume = 1; windows are forward-only (keep_checkpoints == 0).
+                              Lets a caller stream a long record segment by segment (bench.py) the way the
+                              reference's loop feeds dpLGAR.forward one row at a time
+                              (agents/DifferentiableLGAR.py:117-125)                                       */
   int64_t iter_cap;        /* root-finder iteration cap (0 = default 1,000,000)                 */
   double subcycle_length_h;   /* dt in hours                 cfg.models.subcycle_length_h       */
   double wilting_point_psi;   /* cm                          cfg.data.wilting_point_psi         */

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # LGAR_B200_LIB: developer override used to A/B two builds of the same library on one GPU box
 LIB_PATH = os.environ.get("LGAR_B200_LIB") or os.path.join(_HERE, "liblgar_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_LAYERS, MAX_FRONTS, MAX_GIUH, NUM_OUTPUTS = 4, 16, 8, 10
 OUT_NAMES = ("runoff", "percolation", "AET", "infiltration", "ending_volume", "ponded_water",
              "giuh_runoff", "precip", "PET", "discharge")
@@ -30,7 +30,8 @@ class Problem(C.Structure):
         ("abi_version", C.c_int32), ("num_columns", C.c_int32), ("num_layers", C.c_int32),
         ("num_steps", C.c_int32), ("num_subcycles", C.c_int32), ("num_sites", C.c_int32),
         ("nint", C.c_int32), ("num_giuh", C.c_int32), ("max_fronts", C.c_int32),
-        ("chunk_steps", C.c_int32), ("resume", C.c_int32), ("use_closed_form_G", C.c_int32), ("iter_cap", C.c_int64),
+        ("chunk_steps", C.c_int32), ("resume", C.c_int32), ("use_closed_form_G", C.c_int32),
+        ("step_begin", C.c_int32), ("step_end", C.c_int32), ("iter_cap", C.c_int64),
         ("subcycle_length_h", C.c_double), ("wilting_point_psi", C.c_double),
         ("frozen_factor", C.c_double), ("giuh_ordinates", C.c_double * MAX_GIUH),
         ("alpha", _dp), ("n", _dp), ("ksat", _dp), ("theta_r", _dp), ("theta_e", _dp),

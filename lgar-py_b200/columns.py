@@ -177,15 +177,25 @@ def _rerun_overflowed(ens: ColumnEnsemble, alpha, n, ksat, res: "ForwardResult",
 
 def forward_raw(ens: ColumnEnsemble, alpha, n, ksat, outputs=("runoff", "percolation"), per_step=True,
                 num_fronts=False, dump_fronts=False, counters=False, tile_cycles=False, keep_checkpoints=False,
-                workspace: Optional[torch.Tensor] = None, overflow_fallback=False) -> tuple[ForwardResult, torch.Tensor]:
+                workspace: Optional[torch.Tensor] = None, overflow_fallback=False, window=None,
+                into: Optional[ForwardResult] = None) -> tuple[ForwardResult, torch.Tensor]:
     """One persistent launch over all columns and all forcing steps (no autograd).
     overflow_fallback: rerun the columns that overflowed the front list with the 32-front kernel (synchronises:
-    the status array is inspected on the host)."""
+    the status array is inspected on the host).
+    window=(t0, t1): advance only forcing rows [t0, t1) of the record (lgar_problem.step_begin/step_end); t0 > 0
+    continues from the state the previous call left in `workspace` (resume).  Rows of the per-step outputs and
+    crash steps stay absolute, so `into=` (the ForwardResult of the previous window) lets consecutive windows fill
+    one set of buffers; `sums` are the running totals since row 0.  A column that crashed in an EARLIER window
+    reports crash_step = -2 - t (t = the absolute step)."""
     L_ = _capi.lib()
     dev = ens.device
     alpha, n, ksat = _param(alpha, ens), _param(n, ens), _param(ksat, ens)
     B, T = ens.num_columns, ens.num_steps
     p = ens.problem(alpha, n, ksat)
+    if window is not None:
+        p.step_begin, p.step_end = int(window[0]), int(window[1])
+        if p.step_begin > 0:
+            p.resume = 1
     need = L_.lgar_workspace_bytes(C.byref(p), 1 if keep_checkpoints else 0)
     if need == 0:
         _capi.check(-1, "lgar_workspace_bytes")
@@ -193,18 +203,23 @@ def forward_raw(ens: ColumnEnsemble, alpha, n, ksat, outputs=("runoff", "percola
         workspace = torch.empty(need, dtype=torch.uint8, device=dev)
     mask = output_mask(outputs) if per_step else 0
     o = _capi.Outputs()
-    res = ForwardResult(
-        per_step=torch.empty((bin(mask).count("1"), T, B), dtype=F64, device=dev) if mask else None, mask=mask,
-        sums=torch.empty((NUM_OUTPUTS, B), dtype=F64, device=dev),
-        start_volume=torch.empty(B, dtype=F64, device=dev),
-        status=torch.empty(B, dtype=torch.int32, device=dev),
-        crash_step=torch.empty(B, dtype=torch.int32, device=dev))
+    if into is not None:
+        assert into.mask == mask and into.sums.shape[1] == B, "`into` must come from the same ensemble and outputs"
+        res = into
+    else:
+        res = ForwardResult(
+            per_step=torch.empty((bin(mask).count("1"), T, B), dtype=F64, device=dev) if mask else None, mask=mask,
+            sums=torch.empty((NUM_OUTPUTS, B), dtype=F64, device=dev),
+            start_volume=torch.empty(B, dtype=F64, device=dev),
+            status=torch.empty(B, dtype=torch.int32, device=dev),
+            crash_step=torch.empty(B, dtype=torch.int32, device=dev))
     o.per_step = res.per_step.data_ptr() if mask else None
     o.per_step_mask = mask
     o.sums, o.start_volume = res.sums.data_ptr(), res.start_volume.data_ptr()
     o.status, o.crash_step = res.status.data_ptr(), res.crash_step.data_ptr()
     if num_fronts or dump_fronts:
-        res.num_fronts = torch.empty((T, B), dtype=torch.int32, device=dev)
+        if res.num_fronts is None:
+            res.num_fronts = torch.empty((T, B), dtype=torch.int32, device=dev)
         o.num_fronts = res.num_fronts.data_ptr()
     if dump_fronts:
         res.fronts = torch.empty((T, MAX_FRONTS, 5, B), dtype=F64, device=dev)

@@ -31,6 +31,7 @@ int fail(int code, const char* fmt, const char* detail = "") {
 
 struct Shape {
   int B, Bp, L, T, S, FM, chunk, nchunks, ntiles;
+  int t_begin, t_end;  // window of forcing rows (whole record: 0, T)
 };
 
 int shape_of(const lgar_problem* p, Shape& s) {
@@ -49,7 +50,15 @@ int shape_of(const lgar_problem* p, Shape& s) {
   if (s.FM != 8 && s.FM != 12 && s.FM != 16 && s.FM != 32)
     return fail(LGAR_E_INVALID, "max_fronts must be 8, 12, 16 or 32");
   s.chunk = p->chunk_steps > 0 ? p->chunk_steps : 64;
-  s.nchunks = (s.T + s.chunk - 1) / s.chunk;
+  s.t_begin = 0;
+  s.t_end = s.T;
+  if (p->step_begin != 0 || p->step_end != 0) {
+    if (p->step_begin < 0 || p->step_end <= p->step_begin || p->step_end > s.T)
+      return fail(LGAR_E_INVALID, "step window must satisfy 0 <= step_begin < step_end <= num_steps");
+    s.t_begin = p->step_begin;
+    s.t_end = p->step_end;
+  }
+  s.nchunks = (s.t_end - s.t_begin + s.chunk - 1) / s.chunk;
   s.ntiles = s.Bp / 32;
   return 0;
 }
@@ -202,6 +211,9 @@ int lgar_forward(const lgar_problem* p, const lgar_outputs* out, void* workspace
   if (p->num_sites < 1) return fail(LGAR_E_INVALID, "num_sites < 1");
   if (p->resume && keep_checkpoints) return fail(LGAR_E_INVALID, "resume is not available with keep_checkpoints");
   if (s.FM == 32 && keep_checkpoints) return fail(LGAR_E_INVALID, "max_fronts = 32 is forward-only (no checkpoints)");
+  if (keep_checkpoints && (s.t_begin != 0 || s.t_end != s.T))
+    return fail(LGAR_E_INVALID, "a step window is forward-only (keep_checkpoints needs the whole record)");
+  if (s.t_begin != 0 && !p->resume) return fail(LGAR_E_INVALID, "a window that does not start at row 0 needs resume = 1");
   int dev = -1;
   if (cudaGetDevice(&dev) != cudaSuccess || dev != g_dev_checked) {
     rc = lgar_device_check();
@@ -225,6 +237,8 @@ int lgar_forward(const lgar_problem* p, const lgar_outputs* out, void* workspace
   K.ntiles = s.ntiles;
   K.nchunks = s.nchunks;
   K.chunk_steps = s.chunk;
+  K.t_begin = s.t_begin;
+  K.t_end = s.t_end;
   K.keep_ckpt = keep_checkpoints ? 1 : 0;
   K.iter_cap = p->iter_cap > 0 ? p->iter_cap : 1000000;
   CUDA_TRY(cudaMemsetAsync(w + c.off_done, 0, c.total - c.off_done, st));
@@ -279,6 +293,9 @@ int lgar_backward(const lgar_problem* p, const double* grad_per_step, uint32_t g
   K.ntiles = s.ntiles;
   K.nchunks = s.nchunks;
   K.chunk_steps = s.chunk;
+  K.t_begin = 0;
+  K.t_end = s.T;
+  if (s.t_begin != 0 || s.t_end != s.T) return fail(LGAR_E_INVALID, "lgar_backward needs the whole record (no step window)");
   K.keep_ckpt = 1;
   K.iter_cap = p->iter_cap > 0 ? p->iter_cap : 1000000;
   P.grad_per_step = grad_per_step;

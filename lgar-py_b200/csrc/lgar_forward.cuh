@@ -39,6 +39,7 @@ struct KParams {
   unsigned long long* next_item;
   int32_t Bp;            // B rounded up to a multiple of 32
   int32_t ntiles, nchunks, chunk_steps;
+  int32_t t_begin, t_end;  // window of forcing rows advanced by this launch (lgar_problem.step_begin / step_end)
   int32_t keep_ckpt;     // 1: state of chunk c is stored at index c (+ final at nchunks)
   long long iter_cap;
 };
@@ -495,8 +496,8 @@ __global__ void __launch_bounds__(NT, (FM == 32) ? 1 : ((FM == 16) ? 2 : ((FM ==
     precompute_psi_wp(T, p.wilting_point_psi);
     const int site = (p.site_index && valid) ? __ldg(p.site_index + b) : 0;
     const double* frc = p.forcing + (size_t)site * Tn * 2;
-    const int t0 = chunk * K.chunk_steps;
-    const int t1 = min(Tn, t0 + K.chunk_steps);
+    const int t0 = K.t_begin + chunk * K.chunk_steps;
+    const int t1 = min(K.t_end, t0 + K.chunk_steps);
 
     for (int t = t0; t < t1; t++) {
       const double2 x = __ldg(reinterpret_cast<const double2*>(frc) + t);

@@ -28,6 +28,7 @@
 #include <atomic>
 #include <memory>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #define LGAR_LMAX 8
@@ -1231,34 +1232,79 @@ int lgar_oracle_forward_tangent(const lgar_oracle_cfg* cfg, const double* forcin
   return status;
 }
 
-// Many columns sharing one forcing record, std::thread workers over columns (used as the CPU baseline).
-// cfgs[B]; sums[B][NOUT] = per-column sums over time of the per-step outputs (ending_volume
-// and ponded_water: last value); status[B].
-int lgar_oracle_forward_batch(const lgar_oracle_cfg* cfgs, int B, const double* forcing, int T_, double* sums,
-                              int32_t* status, int nthreads) {
+// Many columns, std::thread workers over columns (the CPU baseline of bench.py and the wide parity tests).
+// cfgs[B]; column b reads the forcing record forcing + site[b] * T * 2 (site == NULL: all use record 0);
+// sums[B][NOUT] = per-column sums over time of the per-step outputs of the COMPLETED steps (ending_volume and
+// ponded_water: last value); status[B]; crash_step[B] = forcing step at which the reference raises (-1 = none).
+// dsums (optional) [B][NOUT][3L]: forward-mode tangents of `sums` w.r.t. (alpha[L], n[L], ksat[L]) -- the
+// reference-autograd semantics of the Dual scalar; the forward+gradient CPU baseline.
+}  // extern "C"
+template <class T>
+static void batch_column(const lgar_oracle_cfg& cfg, const double* forcing, int T_, double* sums, double* dsums,
+                         int32_t* status, int32_t* crash_step) {
+  const int L = cfg.num_layers, np = 3 * L;
+  Column<T> col;
+  int st = ST_OK, crash = -1;
+  double acc[LGAR_NOUT] = {0};
+  std::vector<double> dacc, dtmp;
+  constexpr bool TAN = !std::is_same<T, double>::value;
+  if (TAN) {
+    dacc.assign((size_t)LGAR_NOUT * np, 0.0);
+    dtmp.assign((size_t)LGAR_NOUT * np, 0.0);
+  }
+  int t = 0;
+  try {
+    if constexpr (TAN) {
+      Dual a[LGAR_LMAX], n[LGAR_LMAX], k[LGAR_LMAX];
+      for (int l = 0; l < L; l++) {
+        a[l] = Dual(cfg.alpha[l]); a[l].d[l] = 1.0;
+        n[l] = Dual(cfg.n[l]); n[l].d[L + l] = 1.0;
+        k[l] = Dual(cfg.ksat[l]); k[l].d[2 * L + l] = 1.0;
+      }
+      col.init(cfg, a, n, k);
+    } else {
+      col.init(cfg, cfg.alpha, cfg.n, cfg.ksat);
+    }
+    for (t = 0; t < T_; t++) {
+      col.forward(forcing[2 * t], forcing[2 * t + 1]);
+      double o[LGAR_NOUT];
+      store_out(col, o);
+      for (int k = 0; k < LGAR_NOUT; k++) acc[k] = (k == 4 || k == 5) ? o[k] : acc[k] + o[k];
+      if constexpr (TAN) {
+        store_tan(col, dtmp.data(), np);
+        for (int k = 0; k < LGAR_NOUT; k++)
+          for (int q = 0; q < np; q++)
+            dacc[k * np + q] = (k == 4 || k == 5) ? dtmp[k * np + q] : dacc[k * np + q] + dtmp[k * np + q];
+      }
+      col.reset_accumulators();
+    }
+  } catch (RefError& e) {
+    st = e.code;
+    crash = t;
+  }
+  if (sums) std::memcpy(sums, acc, sizeof(acc));
+  if (TAN && dsums) std::memcpy(dsums, dacc.data(), dacc.size() * sizeof(double));
+  if (status) *status = st;
+  if (crash_step) *crash_step = crash;
+}
+
+extern "C" {
+int lgar_oracle_forward_batch_ex(const lgar_oracle_cfg* cfgs, int B, const double* forcing, const int32_t* site, int T_,
+                                 double* sums, double* dsums, int32_t* status, int32_t* crash_step, int nthreads) {
   if (nthreads < 1) nthreads = 1;
   std::atomic<int> next(0);
   auto work = [&]() {
     for (;;) {
       int b = next.fetch_add(1);
       if (b >= B) return;
-      Column<double> col;
-      int st = ST_OK;
-      double acc[LGAR_NOUT] = {0};
-      try {
-        col.init(cfgs[b], cfgs[b].alpha, cfgs[b].n, cfgs[b].ksat);
-        for (int t = 0; t < T_; t++) {
-          col.forward(forcing[2 * t], forcing[2 * t + 1]);
-          double o[LGAR_NOUT];
-          store_out(col, o);
-          for (int k = 0; k < LGAR_NOUT; k++) acc[k] = (k == 4 || k == 5) ? o[k] : acc[k] + o[k];
-          col.reset_accumulators();
-        }
-      } catch (RefError& e) {
-        st = e.code;
-      }
-      if (sums) std::memcpy(sums + (size_t)b * LGAR_NOUT, acc, sizeof(acc));
-      if (status) status[b] = st;
+      const double* f = forcing + (site ? (size_t)site[b] * T_ * 2 : 0);
+      const int np = 3 * cfgs[b].num_layers;
+      if (dsums)
+        batch_column<Dual>(cfgs[b], f, T_, sums ? sums + (size_t)b * LGAR_NOUT : nullptr, dsums + (size_t)b * LGAR_NOUT * np,
+                           status ? status + b : nullptr, crash_step ? crash_step + b : nullptr);
+      else
+        batch_column<double>(cfgs[b], f, T_, sums ? sums + (size_t)b * LGAR_NOUT : nullptr, nullptr,
+                             status ? status + b : nullptr, crash_step ? crash_step + b : nullptr);
     }
   };
   std::vector<std::thread> th;
@@ -1266,6 +1312,11 @@ int lgar_oracle_forward_batch(const lgar_oracle_cfg* cfgs, int B, const double* 
   work();
   for (auto& t : th) t.join();
   return 0;
+}
+
+int lgar_oracle_forward_batch(const lgar_oracle_cfg* cfgs, int B, const double* forcing, int T_, double* sums,
+                              int32_t* status, int nthreads) {
+  return lgar_oracle_forward_batch_ex(cfgs, B, forcing, nullptr, T_, sums, nullptr, status, nullptr, nthreads);
 }
 
 int lgar_oracle_sizeof_cfg(void) { return (int)sizeof(lgar_oracle_cfg); }

@@ -53,6 +53,7 @@ def lib():
         _lib.lgar_oracle_forward.restype = C.c_int
         _lib.lgar_oracle_forward_tangent.restype = C.c_int
         _lib.lgar_oracle_forward_batch.restype = C.c_int
+        _lib.lgar_oracle_forward_batch_ex.restype = C.c_int
     return _lib
 
 
@@ -136,3 +137,28 @@ def forward_batch(cfgs, forcing: np.ndarray, nthreads: int = 1):
     lib().lgar_oracle_forward_batch(arr, C.c_int(B), _p(forcing, C.c_double), C.c_int(forcing.shape[0]),
                                     _p(sums, C.c_double), _p(status, C.c_int32), C.c_int(nthreads))
     return sums, status
+
+
+def forward_batch_ex(cfgs, forcing: np.ndarray, site=None, nthreads: int = 1, tangents: bool = False):
+    """B columns; `forcing` is [T,2] (shared) or [sites,T,2] with `site[B]` choosing the record of each column.
+    Returns dict(sums[B,NOUT], status[B], crash_step[B]) and, with tangents=True, dsums[B,NOUT,3L]: forward-mode
+    derivatives of the sums w.r.t. (alpha[L], n[L], ksat[L]) with the reference's autograd conventions."""
+    forcing = np.ascontiguousarray(forcing, dtype=np.float64)
+    T = forcing.shape[-2]
+    B = len(cfgs)
+    arr = (OracleCfg * B)(*cfgs)
+    sums = np.zeros((B, NOUT))
+    status = np.zeros(B, dtype=np.int32)
+    crash = np.zeros(B, dtype=np.int32)
+    L = cfgs[0].num_layers if B else 0
+    dsums = np.zeros((B, NOUT, 3 * L)) if tangents else None
+    site_arr = None
+    if forcing.ndim == 3:
+        site_arr = np.ascontiguousarray(site if site is not None else np.zeros(B), dtype=np.int32)
+    lib().lgar_oracle_forward_batch_ex(arr, C.c_int(B), _p(forcing, C.c_double), _p(site_arr, C.c_int32), C.c_int(T),
+                                       _p(sums, C.c_double), _p(dsums, C.c_double), _p(status, C.c_int32),
+                                       _p(crash, C.c_int32), C.c_int(nthreads))
+    r = dict(sums=sums, status=status, crash_step=crash)
+    if tangents:
+        r["dsums"] = dsums
+    return r

@@ -2,8 +2,10 @@
 
 TEST INFRASTRUCTURE ONLY (oracle/).  This module exists to (a) generate the
 golden vectors committed under tests/golden/ and (b) validate the C++ oracle
-(oracle/lgar_oracle.cpp).  It needs /root/reference, so it only works in the
-build container -- nothing in `-m gpu` tests, smoke() or bench.py imports it.
+(oracle/lgar_oracle.cpp).  It reads the reference from /root/reference (build container) or, where that does not exist (the GPU
+box), from the staged copy oracle/_ref/ (oracle/make_ref.sh: unmodified files, git-ignored).  The `-m gpu`
+tests and smoke() never import it; bench.py's `--impl reference` arm runs oracle/time_reference.py (which
+uses this module) in sub-processes to time the real Python reference on the box's host cores.
 
 Recipe:
   * a stub `omegaconf` (oracle/pyref_stub) makes the reference importable;
@@ -21,8 +23,17 @@ import traceback
 
 import numpy as np
 
-REF_ROOT = "/root/reference"
 _HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_ref_root():
+    for cand in (os.environ.get("LGAR_REF_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "dpLGAR")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _find_ref_root()
 FMAX = 16
 
 OUT_KEYS = (
