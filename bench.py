@@ -64,6 +64,8 @@ def parse():
                     help="fraction of the 32-column tiles run through the counting kernel (algorithmic flop)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="A/B: stream-ordered windows (no programmatic dependent launch)")
+    ap.add_argument("--e2e-interleaved", action="store_true", help="A/B: D2H of every segment right behind its launch")
     ap.add_argument("--no-pyref", action="store_true", help="reference arm: skip the Python reference (port only)")
     ap.add_argument("--pyref-rows", type=int, default=0, help="reference arm: forcing rows per step of the Python reference")
     ap.add_argument("--pyref-procs", type=int, default=0, help="reference arm: processes of the Python reference (default min(8, cores))")
@@ -389,9 +391,14 @@ def main():
     # ---- HBM-resident pass, one launch per time segment -------------------------------------------------------
     state = {"res": None, "ws": None}
 
+    pipe = not args.no_pipeline
+
     def run_segment(i, a, n_, k):
+        # consecutive windows are a pipelined sequence (lgar_problem.pipeline_seq): window i+1 starts on the SMs that
+        # window i has drained, so the slowest tiles of a window do not idle the GPU at every step boundary
         t0, t1 = segs[i]
-        r, state["ws"] = forward_raw(ens, a, n_, k, outputs=outs, workspace=state["ws"], window=(t0, t1), into=state["res"])
+        r, state["ws"] = forward_raw(ens, a, n_, k, outputs=outs, workspace=state["ws"], window=(t0, t1), into=state["res"],
+                                     pipeline_seq=(i + 1) if pipe else 0)
         state["res"] = r
         return r
 
@@ -400,14 +407,14 @@ def main():
     barrier()
     sampler = ClockSampler(local, interval=0.25)
     sampler.start()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(nseg + 1)]
-    ev[0].record()
-    for i in range(nseg):
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(nseg):  # nothing else goes on the stream between the K launches
         run_segment(i, d_alpha, d_n, d_ksat)
-        ev[i + 1].record()
+    ev1.record()
     barrier()
-    total_ms = ev[0].elapsed_time(ev[-1])
-    kern_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(nseg)]
+    total_ms = ev0.elapsed_time(ev1)
+    kern_ms = [total_ms]   # the K kernels overlap at their boundaries: only their union is a meaningful duration
     sampler.stop_flag = True
     res = state["res"]
     status = res.status.cpu().numpy()
@@ -445,29 +452,45 @@ def main():
 
         def e2e_pass(count=False):
             nonlocal h2d, d2h
-            a = n_ = k = None
-            for i, (t0, t1) in enumerate(segs):
-                if i == 0:
-                    a = host["alpha"].to(dev, non_blocking=True)
-                    n_ = host["n"].to(dev, non_blocking=True)
-                    k = host["ksat"].to(dev, non_blocking=True)
-                    if count:
-                        h2d += 3 * host["alpha"].numel() * 8
-                ens.forcing[:, t0:t1].copy_(host_seg[i], non_blocking=True)
-                r = run_segment(i, a, n_, k)
-                seg_done = torch.cuda.Event()
-                seg_done.record(main_stream)
+            a = host["alpha"].to(dev, non_blocking=True)
+            n_ = host["n"].to(dev, non_blocking=True)
+            k = host["ksat"].to(dev, non_blocking=True)
+            if count:
+                h2d += 3 * host["alpha"].numel() * 8
+
+            def copy_out(i, r):
+                nonlocal d2h
+                t0, t1 = segs[i]
                 buf = pin[i % 2]
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(seg_done)
-                    done_ev[i % 2].synchronize()  # the previous copy out of this buffer has landed (host may reuse it)
-                    for q in range(len(outs)):  # contiguous [rows, B] blocks: plain cudaMemcpyAsync
-                        buf[q, : t1 - t0].copy_(r.per_step[q, t0:t1], non_blocking=True)
-                    done_ev[i % 2].record(copy_stream)
+                done_ev[i % 2].synchronize()  # the previous copy into this staging buffer has landed (host may reuse it)
+                for q in range(len(outs)):    # contiguous [rows, B] blocks: plain cudaMemcpyAsync
+                    buf[q, : t1 - t0].copy_(r.per_step[q, t0:t1], non_blocking=True)
+                done_ev[i % 2].record(torch.cuda.current_stream(dev))
                 if count:
-                    h2d += host_seg[i].numel() * 8
                     d2h += len(outs) * (t1 - t0) * B * 8
-            main_stream.wait_stream(copy_stream)
+
+            if args.e2e_interleaved:
+                for i, (t0, t1) in enumerate(segs):
+                    ens.forcing[:, t0:t1].copy_(host_seg[i], non_blocking=True)
+                    r = run_segment(i, a, n_, k)
+                    seg_done = torch.cuda.Event()
+                    seg_done.record(main_stream)
+                    with torch.cuda.stream(copy_stream):
+                        copy_stream.wait_event(seg_done)
+                        copy_out(i, r)
+                    if count:
+                        h2d += host_seg[i].numel() * 8
+                main_stream.wait_stream(copy_stream)
+            else:
+                # the whole forcing record is 16 B per site-step: copy it up front, launch the K windows back to back
+                # (pipelined), then stream the per-step series out through two bounded pinned staging buffers
+                ens.forcing.copy_(host["forcing"], non_blocking=True)
+                if count:
+                    h2d += host["forcing"].numel() * 8
+                for i in range(nseg):
+                    r = run_segment(i, a, n_, k)
+                for i in range(nseg):
+                    copy_out(i, r)
             out = (r.sums.cpu(), r.status.cpu(), r.crash_step.cpu())
             if count:
                 d2h += out[0].numel() * 8 + out[1].numel() * 4 + out[2].numel() * 4
@@ -569,7 +592,8 @@ def main():
         "data": "synthetic",
         "config": {"workload": workload_name(args), "columns_per_gpu": B, "forcing_steps": T,
                    "step": f"one time segment of {segs[0][1] - segs[0][0]} forcing rows over the whole shard; the {nseg} timed steps are "
-                           "one pass over the full record (resume launches, bit-identical to one launch)",
+                           "one pass over the full record (resume launches, bit-identical to one launch)"
+                           + ("; consecutive windows are pipelined with programmatic dependent launch" if pipe else ""),
                    "ok_fraction": float((status == 0).mean()), "status_histogram": hist,
                    "status_note": "non-OK columns are the reference's exceptions at the same step (it aborts the run); "
                                   "FRONT_OVERFLOW (>16 fronts) and ITER_CAP (a root finder above 1e6 iterations, where the "
@@ -609,8 +633,11 @@ def main():
     if e2e:
         line["e2e"] = {"value": alive_all / (e2e_ms_all * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e[1],
                        "d2h_bytes_per_step": e2e[2], "ms_per_step": e2e_ms_all / nseg, "bit_identical_to_resident_pass": e2e[3],
-                       "what": "forward_raw per segment: pinned forcing segment H2D (+ parameters at step 0), launch, D2H of the "
-                               "segment's per-step runoff and AET (double-buffered on a copy stream), sums/status/crash_step at the end"}
+                       "what": ("forward_raw per segment: pinned forcing segment H2D (+ parameters at step 0), launch, D2H of the segment's "
+                                "per-step runoff and AET on a copy stream, sums/status/crash_step at the end") if args.e2e_interleaved else
+                               ("pinned parameters + forcing record H2D, the K window launches back to back (pipelined), D2H of the per-step "
+                                "runoff and AET series through two pinned staging buffers, then sums/status/crash_step; bytes are per step "
+                                "(= total / K)")}
     if cpu:
         alive_c, dt_c, _, ncol, threads = cpu
         line["cpu_baseline"] = {"value": alive_c / dt_c, "unit": UNIT, "cores": threads, "kind": "port",

@@ -110,6 +110,17 @@ typedef struct lgar_problem {
                               Lets a caller stream a long record segment by segment (bench.py) the way the
                               reference's loop feeds dpLGAR.forward one row at a time
                               (agents/DifferentiableLGAR.py:117-125)                                       */
+  int32_t pipeline_seq;    /* 0: every call is stream-ordered after the previous one (default).
+                              k >= 1: the k-th call of a PIPELINED sequence of consecutive windows of one
+                              record on one stream and workspace (window k starts at the row where window
+                              k-1 ended; k = 1 starts the sequence).  Calls k > 1 are launched with
+                              programmatic dependent launch: their CTAs start on the SMs the previous
+                              window has already drained, and the per-tile progress counters in the
+                              workspace order the column states, so the slowest columns of one window no
+                              longer idle the GPU before the next.  Nothing else may be enqueued on the
+                              stream between two calls of a sequence (it would serialise them again); the
+                              results of all windows are complete when the stream has drained.           */
+  int32_t reserved1;
   int64_t iter_cap;        /* root-finder iteration cap (0 = default 1,000,000)                 */
   double subcycle_length_h;   /* dt in hours                 cfg.models.subcycle_length_h       */
   double wilting_point_psi;   /* cm                          cfg.data.wilting_point_psi         */

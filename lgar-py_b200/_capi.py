@@ -31,7 +31,8 @@ class Problem(C.Structure):
         ("num_steps", C.c_int32), ("num_subcycles", C.c_int32), ("num_sites", C.c_int32),
         ("nint", C.c_int32), ("num_giuh", C.c_int32), ("max_fronts", C.c_int32),
         ("chunk_steps", C.c_int32), ("resume", C.c_int32), ("use_closed_form_G", C.c_int32),
-        ("step_begin", C.c_int32), ("step_end", C.c_int32), ("iter_cap", C.c_int64),
+        ("step_begin", C.c_int32), ("step_end", C.c_int32), ("pipeline_seq", C.c_int32), ("reserved1", C.c_int32),
+        ("iter_cap", C.c_int64),
         ("subcycle_length_h", C.c_double), ("wilting_point_psi", C.c_double),
         ("frozen_factor", C.c_double), ("giuh_ordinates", C.c_double * MAX_GIUH),
         ("alpha", _dp), ("n", _dp), ("ksat", _dp), ("theta_r", _dp), ("theta_e", _dp),

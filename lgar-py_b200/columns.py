@@ -178,7 +178,7 @@ def _rerun_overflowed(ens: ColumnEnsemble, alpha, n, ksat, res: "ForwardResult",
 def forward_raw(ens: ColumnEnsemble, alpha, n, ksat, outputs=("runoff", "percolation"), per_step=True,
                 num_fronts=False, dump_fronts=False, counters=False, tile_cycles=False, keep_checkpoints=False,
                 workspace: Optional[torch.Tensor] = None, overflow_fallback=False, window=None,
-                into: Optional[ForwardResult] = None) -> tuple[ForwardResult, torch.Tensor]:
+                into: Optional[ForwardResult] = None, pipeline_seq: int = 0) -> tuple[ForwardResult, torch.Tensor]:
     """One persistent launch over all columns and all forcing steps (no autograd).
     overflow_fallback: rerun the columns that overflowed the front list with the 32-front kernel (synchronises:
     the status array is inspected on the host).
@@ -186,7 +186,10 @@ def forward_raw(ens: ColumnEnsemble, alpha, n, ksat, outputs=("runoff", "percola
     continues from the state the previous call left in `workspace` (resume).  Rows of the per-step outputs and
     crash steps stay absolute, so `into=` (the ForwardResult of the previous window) lets consecutive windows fill
     one set of buffers; `sums` are the running totals since row 0.  A column that crashed in an EARLIER window
-    reports crash_step = -2 - t (t = the absolute step)."""
+    reports crash_step = -2 - t (t = the absolute step).
+    pipeline_seq=k (1, 2, ...): the k-th consecutive window of a pipelined sequence (lgar_problem.pipeline_seq):
+    windows k > 1 start on the SMs the previous window has drained (programmatic dependent launch); enqueue nothing
+    else on the stream between them."""
     L_ = _capi.lib()
     dev = ens.device
     alpha, n, ksat = _param(alpha, ens), _param(n, ens), _param(ksat, ens)
@@ -196,6 +199,7 @@ def forward_raw(ens: ColumnEnsemble, alpha, n, ksat, outputs=("runoff", "percola
         p.step_begin, p.step_end = int(window[0]), int(window[1])
         if p.step_begin > 0:
             p.resume = 1
+    p.pipeline_seq = int(pipeline_seq)
     need = L_.lgar_workspace_bytes(C.byref(p), 1 if keep_checkpoints else 0)
     if need == 0:
         _capi.check(-1, "lgar_workspace_bytes")

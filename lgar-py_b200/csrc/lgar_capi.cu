@@ -112,8 +112,21 @@ size_t smem_bytes() {
          (size_t)FM * lgar::NT;
 }
 
+// Launch plan of one lgar_forward call.  `pipeline_seq` k > 1 asks for a programmatic dependent launch behind
+// window k-1 (no host memset between the kernels; see KParams::seq).  That is only sound while every launch of
+// the sequence fills the device: then launch k-2 has left the SMs before launch k can become resident, so a ring
+// of three ticket words is enough.  Smaller grids fall back to ordinary stream-ordered launches.
+struct Plan {
+  lgar::KParams K;
+  const Carve* carve;
+  unsigned char* w;
+  int pipeline_seq;
+  bool counters_reset;
+};
+
 template <int FM, bool COUNT, bool DUMP>
-int launch_forward(const lgar::KParams& K, cudaStream_t st) {
+int launch_forward(Plan& P, cudaStream_t st) {
+  lgar::KParams& K = P.K;
   auto kern = lgar::lgar_forward_kernel<FM, COUNT, DUMP>;
   const size_t smem = smem_bytes<FM>();
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -121,10 +134,28 @@ int launch_forward(const lgar::KParams& K, cudaStream_t st) {
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, lgar::NT, smem));
   if (per_sm < 1) return fail(LGAR_E_CUDA, "forward kernel does not fit on an SM");
   long long want = ((long long)K.ntiles * K.nchunks + lgar::WARPS - 1) / lgar::WARPS;
-  long long grid = (long long)g_num_sms * per_sm;
+  const long long full = (long long)g_num_sms * per_sm;
+  long long grid = full;
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, lgar::NT, smem, st>>>(K);
+  const bool pipelined = P.pipeline_seq >= 1 && grid == full;
+  const bool overlap = pipelined && P.pipeline_seq > 1;
+  K.seq = pipelined ? P.pipeline_seq : 0;
+  K.slot = pipelined ? P.pipeline_seq % 3 : 0;
+  K.overlap = overlap ? 1 : 0;
+  if (!overlap)  // progress counters and ticket words start from zero (stream-ordered before the kernel)
+    CUDA_TRY(cudaMemsetAsync(P.w + P.carve->off_done, 0, P.carve->total - P.carve->off_done, st));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(lgar::NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = overlap ? 1 : 0;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, K));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -224,8 +255,15 @@ int lgar_forward(const lgar_problem* p, const lgar_outputs* out, void* workspace
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char* w = (unsigned char*)workspace_dev;
 
-  lgar::KParams K;
+  Plan plan;
+  lgar::KParams& K = plan.K;
   std::memset(&K, 0, sizeof(K));
+  plan.carve = &c;
+  plan.w = w;
+  plan.pipeline_seq = p->pipeline_seq;
+  if (p->pipeline_seq < 0 || p->pipeline_seq >= (1 << 23)) return fail(LGAR_E_INVALID, "pipeline_seq out of range");
+  if (p->pipeline_seq > 0 && keep_checkpoints) return fail(LGAR_E_INVALID, "pipelined windows are forward-only");
+  if (p->pipeline_seq > 1 && !p->resume) return fail(LGAR_E_INVALID, "pipeline_seq > 1 needs resume = 1");
   K.p = *p;
   K.o = *out;
   K.state_d = (double*)(w + c.off_d);
@@ -241,21 +279,22 @@ int lgar_forward(const lgar_problem* p, const lgar_outputs* out, void* workspace
   K.t_end = s.t_end;
   K.keep_ckpt = keep_checkpoints ? 1 : 0;
   K.iter_cap = p->iter_cap > 0 ? p->iter_cap : 1000000;
-  CUDA_TRY(cudaMemsetAsync(w + c.off_done, 0, c.total - c.off_done, st));
-  if (out->counters) CUDA_TRY(cudaMemsetAsync(out->counters, 0, 16 * sizeof(unsigned long long), st));
-  if (out->tile_cycles)
-    CUDA_TRY(cudaMemsetAsync(out->tile_cycles, 0, (size_t)s.ntiles * sizeof(unsigned long long), st));
+  if (p->pipeline_seq <= 1) {  // (a memset between two kernels of a pipelined sequence would serialise them)
+    if (out->counters) CUDA_TRY(cudaMemsetAsync(out->counters, 0, 16 * sizeof(unsigned long long), st));
+    if (out->tile_cycles)
+      CUDA_TRY(cudaMemsetAsync(out->tile_cycles, 0, (size_t)s.ntiles * sizeof(unsigned long long), st));
+  }
   // the kernels without work counters are trapezoid-only (closed-form branch compiled out of the hot path)
   const bool count = out->counters != nullptr || p->use_closed_form_G != 0;
   const bool dump = out->fronts != nullptr;
   if (dump && s.FM != 16) return fail(LGAR_E_INVALID, "front dumps need max_fronts = 16");
 #define LGAR_DISPATCH(FM_)                                                         \
-  if (count) rc = launch_forward<FM_, true, false>(K, st);                         \
-  else rc = launch_forward<FM_, false, false>(K, st);
-  if (dump) rc = launch_forward<16, true, true>(K, st);
+  if (count) rc = launch_forward<FM_, true, false>(plan, st);                      \
+  else rc = launch_forward<FM_, false, false>(plan, st);
+  if (dump) rc = launch_forward<16, true, true>(plan, st);
   else if (s.FM == 8) { LGAR_DISPATCH(8) }
   else if (s.FM == 12) { LGAR_DISPATCH(12) }
-  else if (s.FM == 32) rc = launch_forward<32, true, false>(K, st);  // large-capacity fallback (1 CTA per SM)
+  else if (s.FM == 32) rc = launch_forward<32, true, false>(plan, st);  // large-capacity fallback (1 CTA per SM)
   else { LGAR_DISPATCH(16) }
 #undef LGAR_DISPATCH
   return rc;

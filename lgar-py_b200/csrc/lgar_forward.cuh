@@ -40,6 +40,13 @@ struct KParams {
   int32_t Bp;            // B rounded up to a multiple of 32
   int32_t ntiles, nchunks, chunk_steps;
   int32_t t_begin, t_end;  // window of forcing rows advanced by this launch (lgar_problem.step_begin / step_end)
+  // work-item tickets: 64-bit word next_item[slot] = (epoch << 40) | items handed out.  Classic launches: epoch 0, the
+  // host zeroes the word.  Pipelined launches (lgar_problem.pipeline_seq = k > 1, programmatic dependent launch): no
+  // host memset may sit between the kernels, so block 0 publishes (k << 40) itself and the other warps wait for
+  // their epoch; a warp that finds a NEWER epoch in its slot (ring of 3, only possible for a launch that is over)
+  // leaves.  `overlap`: the previous window may still be running, so even the first chunk of a tile waits for the
+  // tile's progress counter.
+  int32_t seq, slot, overlap;
   int32_t keep_ckpt;     // 1: state of chunk c is stored at index c (+ final at nchunks)
   long long iter_cap;
 };
@@ -445,6 +452,15 @@ __global__ void __launch_bounds__(NT, (FM == 32) ? 1 : ((FM == 16) ? 2 : ((FM ==
   const int S = p.num_subcycles;
   const size_t B = p.num_columns;
   const unsigned long long nitems = (unsigned long long)K.ntiles * K.nchunks;
+  constexpr unsigned long long TICKET_MASK = (1ULL << 40) - 1ULL;
+  unsigned long long* const ticket = K.next_item + K.slot;
+  if (K.seq > 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+    atomicExch(ticket, (unsigned long long)K.seq << 40);
+    __threadfence();
+  }
+  // programmatic dependent launch: the next window's grid may be scheduled as soon as every CTA of this one is
+  // resident (has passed this point) and SM resources free up, i.e. while this launch drains its last items
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   Tile<FM, double> T;
   T.col.fb = sm_fields + threadIdx.x;
@@ -453,7 +469,26 @@ __global__ void __launch_bounds__(NT, (FM == 32) ? 1 : ((FM == 16) ? 2 : ((FM ==
   T.ctx.iter_cap = K.iter_cap;
 
   for (;;) {
-    if (lane == 0) sm_item[warp] = atomicAdd(K.next_item, 1ULL);
+    if (lane == 0) {
+      unsigned long long got = ~0ULL;
+      for (;;) {
+        const unsigned long long v = *reinterpret_cast<volatile unsigned long long*>(ticket);
+        const unsigned long long ep = v >> 40;
+        if (ep != (unsigned long long)K.seq) {
+          if (ep < (unsigned long long)K.seq) {  // block 0 has not published this launch's epoch yet
+            __nanosleep(100);
+            continue;
+          }
+          break;  // the slot belongs to a later launch: this one is over
+        }
+        if ((v & TICKET_MASK) >= nitems) break;
+        if (atomicCAS(ticket, v, v + 1ULL) == v) {
+          got = v & TICKET_MASK;
+          break;
+        }
+      }
+      sm_item[warp] = got;
+    }
     __syncwarp();
     const unsigned long long item = sm_item[warp];
     __syncwarp();
@@ -464,11 +499,13 @@ __global__ void __launch_bounds__(NT, (FM == 32) ? 1 : ((FM == 16) ? 2 : ((FM ==
     const bool valid = (size_t)b < B;
     const int bb = valid ? b : (int)B - 1;  // clamp for loads; results of invalid lanes are never stored
 
-    // wait for the previous chunk of this tile (acquire)
-    if (chunk > 0) {
+    // wait for the previous chunk of this tile (acquire): done[tile] = forcing rows completed (absolute row index)
+    const int t0 = K.t_begin + chunk * K.chunk_steps;
+    const int t1 = min(K.t_end, t0 + K.chunk_steps);
+    if (chunk > 0 || K.overlap) {
       if (lane == 0) {
         volatile int32_t* d = K.done + tile;
-        while (*d < chunk) __nanosleep(200);
+        while (*d < t0) __nanosleep(200);
       }
       __syncwarp();
       __threadfence();
@@ -496,8 +533,6 @@ __global__ void __launch_bounds__(NT, (FM == 32) ? 1 : ((FM == 16) ? 2 : ((FM ==
     precompute_psi_wp(T, p.wilting_point_psi);
     const int site = (p.site_index && valid) ? __ldg(p.site_index + b) : 0;
     const double* frc = p.forcing + (size_t)site * Tn * 2;
-    const int t0 = K.t_begin + chunk * K.chunk_steps;
-    const int t1 = min(K.t_end, t0 + K.chunk_steps);
 
     for (int t = t0; t < t1; t++) {
       const double2 x = __ldg(reinterpret_cast<const double2*>(frc) + t);
@@ -562,7 +597,7 @@ __global__ void __launch_bounds__(NT, (FM == 32) ? 1 : ((FM == 16) ? 2 : ((FM ==
     __syncwarp();
     if (lane == 0) {
       if (K.o.tile_cycles) atomicAdd(K.o.tile_cycles + tile, (unsigned long long)(clock64() - clk0));
-      atomicExch(K.done + tile, chunk + 1);
+      atomicExch(K.done + tile, t1);
     }
   }
 }

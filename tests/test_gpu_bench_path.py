@@ -51,6 +51,29 @@ def test_windows_equal_one_launch(nseg):
                           bench.alive_steps_of(full.status.cpu().numpy(), c_full, T))
 
 
+@pytest.mark.parametrize("B,chunk", [(40_000, 16), (40_000, 64), (4097, 64)])
+def test_pipelined_windows_equal_one_launch(B, chunk):
+    """Consecutive windows launched as a pipelined sequence (programmatic dependent launch, lgar_problem.pipeline_seq):
+    window k+1 runs while window k drains; the per-tile progress counters order the column states.  40,000 columns fill
+    the device (the overlapped path); 4097 columns do not (the library falls back to stream-ordered launches)."""
+    from lgar_b200 import forward_raw
+    import bench
+    we, ens = _setup(B=B, T=200, sites=8, rank=2, chunk_steps=chunk)
+    T = ens.num_steps
+    full, _ = forward_raw(ens, we.alpha, we.n, we.ksat, outputs=OUTS)
+    for rep in range(2):   # the second sequence reuses the workspace (ticket epochs restart at 1)
+        res, ws = None, None
+        for i, (t0, t1) in enumerate(bench.segments(T, 5)):
+            res, ws = forward_raw(ens, we.alpha, we.n, we.ksat, outputs=OUTS, workspace=ws, window=(t0, t1), into=res,
+                                  pipeline_seq=i + 1)
+        torch.cuda.synchronize()
+        assert torch.equal(res.status, full.status)
+        assert torch.equal(res.sums.view(torch.int64), full.sums.view(torch.int64))
+        assert torch.equal(res.per_step.view(torch.int64), full.per_step.view(torch.int64))
+        c = res.crash_step.cpu().numpy()
+        np.testing.assert_array_equal(np.where(c <= -2, -2 - c, c), full.crash_step.cpu().numpy())
+
+
 def test_window_argument_checks():
     from lgar_b200 import forward_raw, LGARLibraryError
     we, ens = _setup(B=64, T=50, sites=1)
