@@ -85,8 +85,8 @@ template <int FM, int GM>
 __global__ void __launch_bounds__(NT) lgar_backward_kernel(const BParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sm_fields = reinterpret_cast<double*>(smem_raw);                       // [5*FM][NT]
-  double* sm_nodes = sm_fields + 5 * FM * NT;                                    // [WARPS][NODEBUF]
-  short* sm_ids = reinterpret_cast<short*>(sm_nodes + WARPS * NODEBUF);          // [5*FM][NT]
+  double* sm_nodes = sm_fields + 5 * FM * NT;                                    // [WARPS][NODEBUF_TAPED]
+  short* sm_ids = reinterpret_cast<short*>(sm_nodes + WARPS * NODEBUF_TAPED);          // [5*FM][NT]
   uint8_t* sm_flags = reinterpret_cast<uint8_t*>(sm_ids + 5 * FM * NT);          // [FM][NT]
   __shared__ unsigned long long sm_item[WARPS];
   pow_tables_to_shared();
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(NT) lgar_backward_kernel(const BParams P) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int slot = blockIdx.x * WARPS + warp;  // resident-warp scratch slot
-  double* nodebuf = sm_nodes + warp * NODEBUF;
+  double* nodebuf = sm_nodes + warp * NODEBUF_TAPED;
   const int Tn = p.num_steps, S = p.num_subcycles;
   const size_t B = p.num_columns;
   constexpr int NL = num_leaves<FM>();

@@ -32,7 +32,8 @@ namespace lgar {
 
 constexpr int NT = 128;          // threads per CTA (4 warps, each warp an independent tile)
 constexpr int WARPS = NT / 32;
-constexpr int NODEBUF = 136;     // doubles of per-warp scratch for Geff nodes (nint <= 128)
+constexpr int NODEBUF = 136;     // doubles of per-warp scratch: Geff request queue (forward), node buffer of the A/B path
+constexpr int NODEBUF_TAPED = 256;  // taped pass: the queue also returns five partials per request
 constexpr int MAXL = LGAR_MAX_LAYERS;
 constexpr int NGIUH = LGAR_MAX_GIUH;
 constexpr int NOUT = LGAR_NUM_OUTPUTS;
@@ -850,6 +851,354 @@ __device__ Var geff_warpR(bool need, const Var& theta_1, const Var& theta_2, con
 }
 
 // ------------------------------------------------------------------------------------
+// Batched Geff: ONE LANE PER REQUEST (green_ampt.py:19-84, trapezoid branch).
+//
+// A sub-step of a 32-column tile issues ~60 independent Geff(theta_1, theta_2; layer) requests in calc_dzdt (one
+// per moving front of every column) -- ~90 % of all requests -- plus at most one per column in insert_water and in
+// calc_dry_depth.  The requests of a phase are known before any of them is evaluated, so they are written to a
+// per-warp queue of 32 slots and every lane evaluates ONE whole request: the literal loop of the reference
+// (`h2 = h2 + dh`, `geff = geff + (k1 + k2) * (dh / 2)`), four nodes at a time so that four independent pow
+// chains are in flight (pow_core_v<4>).  Against the earlier lanes-as-nodes scheme (geff_warp_core, kept for the
+// A/B build -DLGAR_GEFF_COOP) this needs no reconstruction of the node abscissae (advance_rounded), no node
+// buffer, no closing sum on one lane of 32, and its cost no longer depends on which lanes own the requests: the
+// queue spreads them evenly.  Values are bit-identical (same operations on the same operands in the same order).
+// The soil parameters of the requesting column are fetched with warp shuffles (owner lane, list layer).
+// ------------------------------------------------------------------------------------
+struct GeffQueue {         // SoA over the 32 slots of a batch; lives in the per-warp scratch
+  double a[32];            // in: theta_1                    out: Geff
+  double b[32];            // in: theta_2
+  int meta[32];            // in: owner lane | list layer << 8; -1 = empty slot
+  int st[32];              // out: lgar_status raised inside calc_geff (0 = none)
+  double d[5][32];         // out (taped pass only): d Geff / d(theta_1, theta_2, alpha, n, m)
+};
+constexpr int GEFFQ_DOUBLES_FWD = (32 * 8 * 2 + 32 * 4 * 2) / 8;   // forward kernel: without the partials
+constexpr int GEFFQ_DOUBLES_BWD = (int)(sizeof(GeffQueue) / 8);
+
+struct K4 {
+  double k[4];
+  int bad[4];
+};
+// K(Se(h)) at four consecutive trapezoid nodes (the operations of k_nodes_core_x2, four chains interleaved)
+__device__ __forceinline__ void k_nodes_x4(const double (&h)[4], double alpha, double n, double m, double inv_m, double ksat,
+                                           double (&kout)[4], int (&bad)[4]) {
+  bool w[4], ok[4];
+  double x[4], y[4], p[4], u[4], d[4], se[4], sp[4], base[4], o[4];
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    w[e] = fabs(h[e]) < 1.0e-01;
+    x[e] = w[e] ? 1.0 : alpha * h[e];
+    bad[e] = isnan(x[e]) ? LGAR_ST_NAN : (x[e] < 0.0 ? LGAR_ST_NEG_POW : 0);
+    y[e] = n;
+  }
+  pow_core_v<4>(x, y, p, ok);
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    if (!ok[e]) p[e] = pow_slow(x[e], n);
+    u[e] = 1.0 + p[e];
+    y[e] = m;
+  }
+  pow_core_v<4>(u, y, d, ok);
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    if (!ok[e]) d[e] = pow_slow(u[e], m);
+    se[e] = 1.0 / d[e];
+    if (!bad[e] && isnan(se[e])) bad[e] = LGAR_ST_NAN;
+    if (w[e]) se[e] = 1.0;
+    y[e] = inv_m;
+  }
+  pow_core_v<4>(se, y, sp, ok);
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    if (!ok[e]) sp[e] = pow_slow(se[e], inv_m);
+    base[e] = 1.0 - sp[e];
+    if (fabs(base[e]) <= 1e-8) base[e] = base[e] + 1e-12;
+    if (!bad[e]) bad[e] = isnan(base[e]) ? LGAR_ST_NAN : (base[e] < 0.0 ? LGAR_ST_NEG_POW : 0);
+    y[e] = m;
+  }
+  pow_core_v<4>(base, y, o, ok);
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    if (!ok[e]) o[e] = pow_slow(base[e], m);
+    const double t = 1.0 - o[e];
+    if (!bad[e]) bad[e] = isnan(t) ? LGAR_ST_NAN : (t < 0.0 ? LGAR_ST_NEG_POW : 0);
+    kout[e] = ksat * sqrt(se[e]) * (t * t);
+    if (!bad[e] && isnan(kout[e])) bad[e] = LGAR_ST_NAN;
+  }
+}
+
+// gather the soil of (owner lane, list layer) from the lanes' own parameter arrays; warp-convergent
+template <class ST>
+__device__ __forceinline__ Soil gather_soil(const ST* soil, int L, int owner, int lay) {
+  Soil q;
+  q.alpha = q.n = q.m = q.inv_m = q.ninv_m = q.inv_n = q.ksat = q.the = q.thr = 1.0;
+  for (int l = 0; l < L; l++) {
+    const ST& sl = soil[l];
+    const double v0 = shfl_d(sl.alpha, owner), v1 = shfl_d(sl.n, owner), v2 = shfl_d(sl.m, owner);
+    const double v3 = shfl_d(sl.inv_m, owner), v4 = shfl_d(sl.ninv_m, owner), v5 = shfl_d(sl.inv_n, owner);
+    const double v6 = shfl_d(sl.ksat, owner), v7 = shfl_d(sl.the, owner), v8 = shfl_d(sl.thr, owner);
+    if (l == lay) {
+      q.alpha = v0; q.n = v1; q.m = v2; q.inv_m = v3; q.ninv_m = v4; q.inv_n = v5; q.ksat = v6; q.the = v7; q.thr = v8;
+    }
+  }
+  return q;
+}
+
+// Forward (values only).  Every lane of the warp calls it; lane s evaluates slot s.
+template <class ST>
+__device__ __noinline__ void geff_batch_eval(GeffQueue* q, const ST* soil, int L, int nint) {
+  const int lane = threadIdx.x & 31;
+  const int meta = q->meta[lane];
+  const bool have = meta >= 0;
+  const Soil s = gather_soil(soil, L, have ? (meta & 31) : lane, have ? ((meta >> 8) & 7) : 0);
+  if (have) {
+    Ctx c;
+    c.st = 0;
+    const double theta_1 = q->a[lane], theta_2 = q->b[lane];
+    const double se_i = se_from_theta(theta_1, s, c);
+    const double se_f = se_from_theta(theta_2, s, c);
+    const double2 hh = h_from_se_x2(se_i, se_f, s, c);
+    const double h_i = hh.x, h_f = hh.y;
+    // "Checkpoint" calls green_ampt.py:61-63: results unused, only their guards can matter
+    if (fabs(h_i) >= 0.1 && s.alpha * h_i < 0.0) raise(c, LGAR_ST_NEG_POW);
+    if (fabs(h_f) >= 0.1 && s.alpha * h_f < 0.0) raise(c, LGAR_ST_NEG_POW);
+    const double dh = (h_f - h_i) / (double)nint;
+    double k1 = k_from_se(se_i, s.ksat, s.m, s.inv_m, c);
+    const double half = dh / 2.0;
+    double geff = 0.0;
+    double h2 = h_i + dh;
+    int st = c.st;
+    for (int i = 0; i < nint; i += 4) {
+      double h[4], kk[4];
+      int bad[4];
+      h[0] = h2;
+      h[1] = h[0] + dh;
+      h[2] = h[1] + dh;
+      h[3] = h[2] + dh;
+      h2 = h[3] + dh;
+      k_nodes_x4(h, s.alpha, s.n, s.m, s.inv_m, s.ksat, kk, bad);
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        if (i + e < nint) {
+          if (st == 0 && bad[e]) st = bad[e];
+          geff = geff + ((k1 + kk[e]) * half);
+          k1 = kk[e];
+        }
+      }
+    }
+    q->a[lane] = fabs(geff / s.ksat);
+    q->st[lane] = st;
+  }
+  __syncwarp();
+}
+
+// Four trapezoid nodes with everything the reverse kernel needs (k_node_full, four chains interleaved): K and the
+// partials of K(Se(h; alpha, n, m); ksat, m) w.r.t. h, alpha, n, m; the logs are by-products of the pow cores.
+__device__ __forceinline__ void k_node_full_x4(const double (&h)[4], double alpha, double n, double m, double inv_m, double ksat,
+                                               double (&K)[4], double (&dk_h)[4], double (&dk_a)[4], double (&dk_n)[4],
+                                               double (&dk_m)[4], int (&bad)[4]) {
+  bool w[4], ok[4];
+  double x[4], y[4], ap[4], lx[4], u[4], um[4], lu[4], se[4], sp[4], lse[4], base[4], op[4], lb[4];
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    w[e] = fabs(h[e]) < 1.0e-01;
+    x[e] = w[e] ? 1.0 : alpha * h[e];
+    bad[e] = isnan(x[e]) ? LGAR_ST_NAN : (x[e] < 0.0 ? LGAR_ST_NEG_POW : 0);
+    y[e] = n;
+  }
+  pow_core_v<4>(x, y, ap, ok, lx);
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    if (!ok[e]) { ap[e] = pow_slow(x[e], n); lx[e] = log(x[e]); }
+    u[e] = 1.0 + ap[e];
+    y[e] = m;
+  }
+  pow_core_v<4>(u, y, um, ok, lu);
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    if (!ok[e]) { um[e] = pow_slow(u[e], m); lu[e] = log(u[e]); }
+    se[e] = 1.0 / um[e];
+    if (!bad[e] && isnan(se[e])) bad[e] = LGAR_ST_NAN;
+  }
+  double dse_dh[4], dse_da[4], dse_dn[4], dse_dm[4];
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    if (w[e]) {
+      se[e] = 1.0;
+      dse_dh[e] = dse_da[e] = dse_dn[e] = dse_dm[e] = 0.0;
+    } else {
+      const double dse_du = -m * se[e] / u[e];
+      const double dap_dx = (x[e] == 0.0) ? 0.0 : n * ap[e] / x[e];
+      dse_dh[e] = dse_du * dap_dx * alpha;
+      dse_da[e] = dse_du * dap_dx * h[e];
+      dse_dn[e] = (x[e] == 0.0) ? 0.0 : dse_du * ap[e] * lx[e];
+      dse_dm[e] = -se[e] * lu[e];
+    }
+    y[e] = inv_m;
+  }
+  pow_core_v<4>(se, y, sp, ok, lse);
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    if (!ok[e]) { sp[e] = pow_slow(se[e], inv_m); lse[e] = log(se[e]); }
+    base[e] = 1.0 - sp[e];
+    if (fabs(base[e]) <= 1e-8) base[e] = base[e] + 1e-12;
+    if (!bad[e]) bad[e] = isnan(base[e]) ? LGAR_ST_NAN : (base[e] < 0.0 ? LGAR_ST_NEG_POW : 0);
+    y[e] = m;
+  }
+  pow_core_v<4>(base, y, op, ok, lb);
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    if (!ok[e]) { op[e] = pow_slow(base[e], m); lb[e] = log(base[e]); }
+    const double t = 1.0 - op[e];
+    if (!bad[e]) bad[e] = isnan(t) ? LGAR_ST_NAN : (t < 0.0 ? LGAR_ST_NEG_POW : 0);
+    const double rs = sqrt(se[e]);
+    K[e] = ksat * rs * (t * t);
+    if (!bad[e] && isnan(K[e])) bad[e] = LGAR_ST_NAN;
+    // -dop/dse = op sp / (base se);  dop/dm = op ln(base) + op sp ln(se) / (base m)   (k_se_partials_core)
+    const double sp_over = (se[e] == 0.0) ? 0.0 : sp[e] / se[e];
+    const double ndop_dse = op[e] * sp_over / base[e];
+    const double lnse = (se[e] == 0.0) ? 0.0 : lse[e];
+    const double dop_dm = op[e] * lb[e] + op[e] * sp[e] * lnse / (base[e] * m);
+    const double dk_se = ksat * ((rs == 0.0 ? 0.0 : t * t / (2.0 * rs)) + 2.0 * t * rs * ndop_dse);
+    const double dkm = ksat * rs * 2.0 * t * (-dop_dm);
+    dk_h[e] = dk_se * dse_dh[e];
+    dk_a[e] = dk_se * dse_da[e];
+    dk_n[e] = dk_se * dse_dn[e];
+    dk_m[e] = dk_se * dse_dm[e] + dkm;
+  }
+}
+
+// Taped pass: value (the forward kernel's bits) and the partials of Geff w.r.t. theta_1, theta_2, alpha, n, m of
+// one request per lane.  G = dh sum_k w_k K_k, geff = |G / ksat| (d geff / d ksat = 0: K is proportional to ksat);
+// K_k = K(Se(h_k)), h_k = h_i + k dh; node 0 is K(Se_i), a direct function of Se_i in the reference graph
+// (green_ampt.py:75).  The owner lane turns the five partials into one tape entry.
+template <class ST>
+__device__ __noinline__ void geff_batch_eval_taped(GeffQueue* q, const ST* soil, int L, int nint) {
+  const int lane = threadIdx.x & 31;
+  const int meta = q->meta[lane];
+  const bool have = meta >= 0;
+  const Soil s = gather_soil(soil, L, have ? (meta & 31) : lane, have ? ((meta >> 8) & 7) : 0);
+  if (have) {
+    Ctx c;
+    c.st = 0;
+    const double theta_1 = q->a[lane], theta_2 = q->b[lane];
+    const double se_i = se_from_theta(theta_1, s, c);
+    const double se_f = se_from_theta(theta_2, s, c);
+    const double2 hh = h_from_se_x2(se_i, se_f, s, c);
+    const double h_i = hh.x, h_f = hh.y;
+    if (fabs(h_i) >= 0.1 && s.alpha * h_i < 0.0) raise(c, LGAR_ST_NEG_POW);
+    if (fabs(h_f) >= 0.1 && s.alpha * h_f < 0.0) raise(c, LGAR_ST_NEG_POW);
+    const double dh = (h_f - h_i) / (double)nint;
+    double k1 = k_from_se(se_i, s.ksat, s.m, s.inv_m, c);
+    const P4 pi = h_se_partials_core(se_i, s.alpha, s.ninv_m, s.inv_m, s.inv_n, h_i);
+    const P4 pf = h_se_partials_core(se_f, s.alpha, s.ninv_m, s.inv_m, s.inv_n, h_f);
+    const NodeFull n0 = k_node_full(h_i, true, se_i, s.alpha, s.n, s.m, s.inv_m, s.ksat);
+    int st = c.st;
+    if (st == 0 && n0.bad) st = n0.bad;
+    double S = 0.5 * k1, Csei = 0.5 * n0.dk_se, Ahi = 0.0, Ahf = 0.0, Ca = 0.0, Cn = 0.0, Cm = 0.5 * n0.dk_m;
+    const double half = dh / 2.0;
+    const double inv_nint = 1.0 / (double)nint;
+    double geff = 0.0;
+    double h2 = h_i + dh;
+    for (int i = 0; i < nint; i += 4) {
+      double h[4], kk[4], dk_h[4], dk_a[4], dk_n[4], dk_m[4];
+      int bad[4];
+      h[0] = h2;
+      h[1] = h[0] + dh;
+      h[2] = h[1] + dh;
+      h[3] = h[2] + dh;
+      h2 = h[3] + dh;
+      k_node_full_x4(h, s.alpha, s.n, s.m, s.inv_m, s.ksat, kk, dk_h, dk_a, dk_n, dk_m, bad);
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int node = i + e + 1;
+        if (node <= nint) {
+          if (st == 0 && bad[e]) st = bad[e];
+          geff = geff + ((k1 + kk[e]) * half);
+          k1 = kk[e];
+          const double wgt = (node == nint) ? 0.5 : 1.0;
+          const double frac = (double)node * inv_nint;
+          S += wgt * kk[e];
+          Ahi += wgt * dk_h[e] * (1.0 - frac);
+          Ahf += wgt * dk_h[e] * frac;
+          Ca += wgt * dk_a[e];
+          Cn += wgt * dk_n[e];
+          Cm += wgt * dk_m[e];
+        }
+      }
+    }
+    const double value = fabs(geff / s.ksat);
+    const double G = dh * S;
+    const double sg = (G / s.ksat > 0.0) ? 1.0 : ((G / s.ksat < 0.0) ? -1.0 : 0.0);
+    const double f = sg / s.ksat;
+    const double dG_dhi = -S * inv_nint + dh * Ahi;
+    const double dG_dhf = S * inv_nint + dh * Ahf;
+    const double inv_span = 1.0 / (s.the - s.thr);
+    q->a[lane] = value;
+    q->st[lane] = st;
+    q->d[0][lane] = f * (dG_dhi * pi.a + dh * Csei) * inv_span;
+    q->d[1][lane] = f * (dG_dhf * pf.a) * inv_span;
+    q->d[2][lane] = f * (dh * Ca + dG_dhi * pi.b + dG_dhf * pf.b);
+    q->d[3][lane] = f * (dh * Cn + dG_dhi * pi.c + dG_dhf * pf.c);
+    q->d[4][lane] = f * (dh * Cm + dG_dhi * pi.d + dG_dhf * pf.d);
+  }
+  __syncwarp();
+}
+
+// ---- queue protocol shared by the three call sites of a sub-step ------------------------------------------------
+__device__ __forceinline__ void geffq_put(GeffQueue* q, int slot, int owner, int layer, double t1, double t2) {
+  q->a[slot] = t1;
+  q->b[slot] = t2;
+  q->meta[slot] = owner | (layer << 8);
+}
+// result of slot `slot`, owned by this lane (value + status; the taped pass records one entry with five partials)
+__device__ __forceinline__ double geffq_get(GeffQueue* q, int slot, double /*t1*/, double /*t2*/, const SoilT<double>&, int nint,
+                                            Ctx& c) {
+  c.cnt[C_GEFF]++;
+  c.cnt[C_H_SE] += 2;
+  c.cnt[C_K_SE] += 1 + nint;
+  c.cnt[C_SE_H] += nint;
+  const int st = q->st[slot];
+  if (st) raise(c, st);
+  return q->a[slot];
+}
+__device__ __forceinline__ Var geffq_get(GeffQueue* q, int slot, const Var& t1, const Var& t2, const SoilT<Var>& s, int nint,
+                                         Ctx& c) {
+  c.cnt[C_GEFF]++;
+  c.cnt[C_H_SE] += 2;
+  c.cnt[C_K_SE] += 1 + nint;
+  c.cnt[C_SE_H] += nint;
+  const int st = q->st[slot];
+  if (st) raise(c, st);
+  const int ids[5] = {t1.id, t2.id, s.id_alpha, s.id_n, s.id_m};
+  const double d[5] = {q->d[0][slot], q->d[1][slot], q->d[2][slot], q->d[3][slot], q->d[4][slot]};
+  return tape_record_n(q->a[slot], 5, ids, d);
+}
+__device__ __forceinline__ void geffq_eval(GeffQueue* q, const SoilT<double>* soil, int L, int nint) {
+  geff_batch_eval(q, soil, L, nint);
+}
+__device__ __forceinline__ void geffq_eval(GeffQueue* q, const SoilT<Var>* soil, int L, int nint) {
+  geff_batch_eval_taped(q, soil, L, nint);
+}
+
+// At most one request per lane (insert_water, calc_dry_depth): slot = lane.  Warp-convergent.
+template <int GM, class R>
+__device__ __forceinline__ R geff_one_per_lane(bool need, const R& theta_1, const R& theta_2, int layer, const SoilT<R>* soil,
+                                               int L, int nint, GeffQueue* q, Ctx& c) {
+  if (GM == 2 && nint < 0)  // closed form: per lane, no cooperation (geff_warpR handles it)
+    return geff_warpR<GM>(need, theta_1, theta_2, soil[need ? layer : 0], nint, reinterpret_cast<double*>(q), c);
+  if (!__any_sync(0xffffffffu, need)) return R(0.0);
+  const int lane = threadIdx.x & 31;
+  q->meta[lane] = -1;
+  if (need) geffq_put(q, lane, lane, layer, val(theta_1), val(theta_2));
+  __syncwarp();
+  geffq_eval(q, soil, L, nint);
+  R r(0.0);
+  if (need) r = geffq_get(q, lane, theta_1, theta_2, soil[layer], nint, c);
+  __syncwarp();
+  return r;
+}
+
+// ------------------------------------------------------------------------------------
 // Column: per-thread view of the front list in shared memory + scalar state in registers.
 // R = double: forward kernel.  R = Var: taped pass (values in the same shared-memory array, tape
 // ids of the five fields in a parallel int array).
@@ -933,6 +1282,15 @@ struct Column {
   // WettingFront.is_equal (WettingFront.py:76-84): value equality on depth, psi, dzdt (Q3)
   __device__ __forceinline__ bool is_equal(int a, int b) {
     return f(F_DEPTH, a) == f(F_DEPTH, b) && f(F_PSI, a) == f(F_PSI, b) && f(F_DZDT, a) == f(F_DZDT, b);
+  }
+  // list layer of flat front index i
+  __device__ __forceinline__ int list_layer(int i) const {
+    int l = 0, o = cnt(0);
+    while (i >= o && l < MAXL - 1) {
+      l++;
+      o += cnt(l);
+    }
+    return l;
   }
   // Layer.get_len_layers (Layer.py:1145-1155)
   __device__ __forceinline__ int len_layers(int l) const { return (l < L - 1) ? cnt(l) : cnt(l) - 1; }

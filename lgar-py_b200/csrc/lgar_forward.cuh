@@ -127,6 +127,7 @@ __device__ void substep(Tile<FM, R>& T, bool act, double precip_rate, double pet
   const double dt = K.p.subcycle_length_h;
   const int nint = (GM == 2 && K.p.use_closed_form_G) ? -1 : K.p.nint;  // nint < 0 selects the closed-form Geff (geff_warpR)
   const int L = C.L;
+  GeffQueue* const gq = reinterpret_cast<GeffQueue*>(nodebuf);
   act = act && (c.st == 0);
 
   double precip_sub = 0.0;
@@ -169,7 +170,11 @@ __device__ void substep(Tile<FM, R>& T, bool act, double precip_rate, double pet
         theta_2 = R(C.soil[lfp].the);
       }
     }
+#ifdef LGAR_GEFF_COOP
     const R geff = geff_warpR<GM>(needG, theta_1, theta_2, C.soil[needG ? lfp : 0], nint, nodebuf, c);
+#else
+    const R geff = geff_one_per_lane<GM, R>(needG, theta_1, theta_2, lfp, C.soil, K.p.num_layers, nint, gq, c);
+#endif
     if (brB && c.st == 0) {
       const R h_p = clamp_min_((ponded_depth_sub - precip_sub) * dt, 0.0);  // clamp(min=0)
       const R fd_depth = C.g(F_DEPTH, fd);
@@ -234,7 +239,11 @@ __device__ void substep(Tile<FM, R>& T, bool act, double precip_rate, double pet
       theta_1 = C.g(F_THETA, 0);
       theta_2 = R(C.soil[0].the);
     }
+#ifdef LGAR_GEFF_COOP
     const R geff = geff_warpR<GM>(needG, theta_1, theta_2, C.soil[0], nint, nodebuf, c);
+#else
+    const R geff = geff_one_per_lane<GM, R>(needG, theta_1, theta_2, 0, C.soil, K.p.num_layers, nint, gq, c);
+#endif
     if (needG && c.st == 0) {
       const SoilT<R>& s = C.soil[0];
       const R cur_theta = C.g(F_THETA, 0);
@@ -282,8 +291,97 @@ __device__ void substep(Tile<FM, R>& T, bool act, double precip_rate, double pet
   }
 
   if (timed) { const long long t = clock64(); c.ph[2] += (unsigned long long)(t - tph); tph = t; }
-  // ---- phase 4: Layer.calc_dzdt (Layer.py:1176-1252), one cooperative Geff per moving front
-  {
+  // ---- phase 4: Layer.calc_dzdt (Layer.py:1176-1252): one Geff per moving front of every column.  All requests of
+  //      the tile are known here, so they go through the per-warp queue in batches of 32, one lane per request
+  //      (geff_batch_eval); each lane then finishes dzdt of its own fronts in front order.
+#ifndef LGAR_GEFF_COOP
+  if (!(GM == 2 && nint < 0)) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const bool go = act && c.st == 0;
+    const int my_n = go ? C.n - 1 : 0;  // the deepest front of the domain is excluded
+    // requests of this lane: the fronts that are not to_bottom, up to the first front whose pre-checks fail (the
+    // reference raises there, after the fronts before it went through calc_geff)
+    int nreq = 0, pre_err = 0;
+    {
+      int l = 0, o_next = go ? C.cnt(0) : 0;
+      for (int i = 0; i < my_n; i++) {
+        while (i >= o_next) {
+          l++;
+          o_next += C.cnt(l);
+        }
+        if (C.tb(i)) {
+          C.s(F_DZDT, i, R(0.0));
+          continue;
+        }
+        if (C.lay(i) > 0) {
+          if (l == 0) pre_err = LGAR_ST_NULL_NEIGHBOUR;  // self.previous_layer is None
+        } else if (C.f(F_THETA, i + 1) > C.f(F_THETA, i)) {
+          pre_err = LGAR_ST_THETA_ORDER;
+        }
+        if (pre_err) break;
+        nreq++;
+      }
+    }
+    int incl = nreq;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(FULL, incl, d);
+      if (lane >= d) incl += v;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    int g = incl - nreq;   // queue index of this lane's next request
+    int cur = 0;           // next front to look at
+    int rem = nreq;
+    for (int lo = 0; lo < total; lo += 32) {
+      const int hi = lo + 32;
+      gq->meta[lane] = -1;
+      __syncwarp();
+      {
+        int i = cur, gg = g, r_ = rem;
+        while (r_ > 0 && gg < hi) {
+          if (!C.tb(i)) {
+            geffq_put(gq, gg - lo, lane, C.list_layer(i), C.f(F_THETA, i + 1), C.f(F_THETA, i));
+            gg++;
+            r_--;
+          }
+          i++;
+        }
+      }
+      __syncwarp();
+      geffq_eval(gq, C.soil, K.p.num_layers, nint);
+      while (rem > 0 && g < hi) {
+        const int i = cur++;
+        if (C.tb(i)) continue;
+        const int slot = g - lo;
+        g++;
+        rem--;
+        if (c.st != 0) continue;
+        const int l = C.list_layer(i);
+        const R theta_1 = C.g(F_THETA, i + 1), theta_2 = C.g(F_THETA, i);
+        const SoilT<R>& s = C.soil[l];
+        const R geff = geffq_get(gq, slot, theta_1, theta_2, s, nint, c);
+        if (c.st != 0) continue;
+        const R depth = C.g(F_DEPTH, i);
+        const R delta_theta = theta_2 - theta_1;
+        R dzdt(0.0);
+        if (C.lay(i) == 0) {
+          if (delta_theta > 0.0)
+            dzdt = 1.0 / delta_theta * (s.ksatR() * (geff + ponded_depth_sub) / depth + C.g(F_K, i));
+        } else {
+          const R bottom_sum = 0.0 + (C.g(F_DEPTH, i) - C.cum[l - 1]) / C.g(F_K, i);
+          const R denominator = C.calc_bottom_sum(0, bottom_sum, C.g(F_PSI, i), C.lay(i), c);
+          if (delta_theta > 0.0)
+            dzdt = (1.0 / delta_theta) * ((depth / denominator) + s.ksatR() * (geff + ponded_depth_sub) / depth);
+        }
+        C.s(F_DZDT, i, dzdt);
+      }
+      __syncwarp();
+    }
+    if (go && c.st == 0 && pre_err) raise(c, pre_err);
+  } else
+#endif
+  {  // closed-form Geff (per lane) or the A/B build with lanes-as-nodes: one request at a time
     const bool go = act && c.st == 0;
     const int my_n = go ? C.n - 1 : 0;  // the deepest front of the domain is excluded
     int nmax = my_n;
