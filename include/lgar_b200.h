@@ -139,6 +139,12 @@ typedef struct lgar_problem {
   /* forcing, data/Data.py:33-40: x[t] = (P, PET) in cm/h                                       */
   const double* forcing;      /* [num_sites][T][2]                                               */
   const int32_t* site_index;  /* [B] forcing series of each column (NULL = all use series 0)    */
+  const int32_t* column_order; /* [B] permutation of 0..B-1 or NULL: the i-th thread of the launch grid works on
+                              column column_order[i].  Every array of this struct and of lgar_outputs stays
+                              indexed by COLUMN; only the placement of columns on warps changes (results do not
+                              depend on it).  A warp advances its 32 columns in lock step, so grouping columns of
+                              similar cost (e.g. sorted by top-layer ksat) raises lane utilisation.  lgar_backward
+                              and resumed calls must pass the order of the lgar_forward they follow.           */
 } lgar_problem;
 
 /* Output buffers.  Any pointer may be NULL (that output is skipped).                           */

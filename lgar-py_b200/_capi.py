@@ -37,7 +37,7 @@ class Problem(C.Structure):
         ("frozen_factor", C.c_double), ("giuh_ordinates", C.c_double * MAX_GIUH),
         ("alpha", _dp), ("n", _dp), ("ksat", _dp), ("theta_r", _dp), ("theta_e", _dp),
         ("thickness", _dp), ("initial_psi", _dp), ("ponded_depth_max", _dp),
-        ("forcing", _dp), ("site_index", _dp),
+        ("forcing", _dp), ("site_index", _dp), ("column_order", _dp),
     ]
 
 

@@ -57,6 +57,7 @@ class ColumnEnsemble:
     chunk_steps: int = 64
     iter_cap: int = 0
     resume: bool = False             # continue from the state left in the workspace (see lgar_b200.h)
+    column_order: Optional[torch.Tensor] = None  # [B] int32 permutation: placement of columns on warps (lgar_b200.h)
     device: object = "cuda"
     _keep: list = field(default_factory=list, repr=False)
 
@@ -77,6 +78,9 @@ class ColumnEnsemble:
         if self.site_index is not None:
             self.site_index = torch.as_tensor(self.site_index, dtype=torch.int32).to(dev).contiguous()
             assert self.site_index.shape == (B,)
+        if self.column_order is not None:
+            self.column_order = torch.as_tensor(self.column_order, dtype=torch.int32).to(dev).contiguous()
+            assert self.column_order.shape == (B,)
         self.initial_psi = _dev_f64(self.initial_psi, dev, (B,))
         self.ponded_depth_max = _dev_f64(self.ponded_depth_max, dev, (B,))
 
@@ -106,7 +110,24 @@ class ColumnEnsemble:
         p.initial_psi, p.ponded_depth_max = self.initial_psi.data_ptr(), self.ponded_depth_max.data_ptr()
         p.forcing = self.forcing.data_ptr()
         p.site_index = self.site_index.data_ptr() if self.site_index is not None else None
+        p.column_order = self.column_order.data_ptr() if self.column_order is not None else None
         return p
+
+    def balance(self, ksat) -> "ColumnEnsemble":
+        """Place columns of similar cost on the same warp.  A warp advances its 32 columns in lock step, so its time per
+        step is that of its slowest lane.  Two things make lanes alike: (1) the same forcing record -- storms and dry
+        spells then hit all lanes in the same steps (columns of one site stay together); (2) within a site, a similar
+        top-layer conductivity: the number of root-finder iterations of a column follows ksat[0] (rank correlation 0.76
+        on the bench ensemble: a conductive top layer sends the fronts into the deeper layers, where every move is a
+        mass-balance root find).  Sets `column_order` = columns sorted by (site, ksat[0]); results do not depend on
+        the placement (tests/test_gpu_properties.py)."""
+        k0 = torch.as_tensor(ksat, dtype=F64)
+        k0 = (k0[0] if k0.dim() == 2 else k0[0].expand(self.num_columns)).to(self.device)
+        order = torch.argsort(k0, stable=True)
+        if self.site_index is not None:
+            order = order[torch.argsort(self.site_index[order].to(torch.int64), stable=True)]
+        self.column_order = order.to(torch.int32).contiguous()
+        return self
 
 
 def output_mask(names) -> int:

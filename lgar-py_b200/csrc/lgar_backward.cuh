@@ -121,13 +121,15 @@ __global__ void __launch_bounds__(NT) lgar_backward_kernel(const BParams P) {
     const unsigned long long tile = sm_item[warp];
     __syncwarp();
     if (tile >= (unsigned long long)K.ntiles) break;
-    const int b = (int)tile * 32 + lane;
-    const bool valid = (size_t)b < B;
-    const int bb = valid ? b : (int)B - 1;
+    const int slot_c = (int)tile * 32 + lane;   // position in the tile grid (checkpoints); b = ensemble column
+    const bool valid = (size_t)slot_c < B;
+    const int slot_cc = valid ? slot_c : (int)B - 1;
+    const int b = p.column_order ? __ldg(p.column_order + slot_cc) : slot_cc;
+    const int bb = b;
 
     // final status of the forward pass: steps at and after the crash step have no gradient
-    const int final_st = __ldcg(K.state_i + ((size_t)K.nchunks * NI_STATE + 2) * K.Bp + bb);
-    const int final_crash = __ldcg(K.state_i + ((size_t)K.nchunks * NI_STATE + 3) * K.Bp + bb);
+    const int final_st = __ldcg(K.state_i + ((size_t)K.nchunks * NI_STATE + 2) * K.Bp + slot_cc);
+    const int final_crash = __ldcg(K.state_i + ((size_t)K.nchunks * NI_STATE + 3) * K.Bp + slot_cc);
     const int t_end = (final_st == 0) ? Tn : final_crash;  // steps [0, t_end) produced outputs
 
     load_params(K, bb, Tv);
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(NT) lgar_backward_kernel(const BParams P) {
       const int t0 = chunk * K.chunk_steps;
       const int t1 = min(Tn, t0 + K.chunk_steps);
       // ---- forward through the chunk ON THE TAPE, from the checkpoint the forward kernel stored
-      load_state(K, chunk, bb, Tv);
+      load_state(K, chunk, slot_cc, Tv);
       int arena_used = 0;
       for (int t = t0; t < t1; t++) {
         const double2 x = __ldg(reinterpret_cast<const double2*>(frc) + t);

@@ -369,7 +369,7 @@ int lgar_forward_host(const lgar_problem* ph, const lgar_outputs* oh) {
   const size_t LB = (size_t)s.L * s.B, B = s.B, T = s.T;
 #define UP(field, count) if ((rc = db.up(ph->field, (count), &p.field))) return rc;
   UP(alpha, LB) UP(n, LB) UP(ksat, LB) UP(theta_r, LB) UP(theta_e, LB) UP(thickness, LB)
-  UP(initial_psi, B) UP(ponded_depth_max, B) UP(forcing, (size_t)ph->num_sites * T * 2) UP(site_index, B)
+  UP(initial_psi, B) UP(ponded_depth_max, B) UP(forcing, (size_t)ph->num_sites * T * 2) UP(site_index, B) UP(column_order, B)
 #undef UP
 #define AL(field, count) if ((rc = db.alloc(oh->field, (count), &o.field))) return rc;
   AL(per_step, (size_t)__builtin_popcount(oh->per_step_mask) * T * B) AL(sums, (size_t)LGAR_NUM_OUTPUTS * B) AL(start_volume, B)

@@ -967,6 +967,7 @@ __device__ __noinline__ void geff_batch_eval(GeffQueue* q, const ST* soil, int L
     double geff = 0.0;
     double h2 = h_i + dh;
     int st = c.st;
+#ifdef LGAR_GEFF_X4
     for (int i = 0; i < nint; i += 4) {
       double h[4], kk[4];
       int bad[4];
@@ -985,6 +986,27 @@ __device__ __noinline__ void geff_batch_eval(GeffQueue* q, const ST* soil, int L
         }
       }
     }
+#else
+    // two nodes per pass through the SAME out-of-line pair evaluator as everything else (k_nodes_core_x2 -> pow_x2):
+    // the kernel is instruction-fetch sensitive, so the hot loops share one small body of pow code
+#pragma unroll 1
+    for (int i = 0; i < nint; i += 2) {
+      const double ha = h2, hb = ha + dh;
+      h2 = hb + dh;
+      int bad;
+      const double2 kk = k_nodes_core_x2(ha, hb, s.alpha, s.n, s.m, s.inv_m, s.ksat, &bad);
+      geff = geff + ((k1 + kk.x) * half);
+      k1 = kk.x;
+      if (i + 1 < nint) {
+        geff = geff + ((k1 + kk.y) * half);
+        k1 = kk.y;
+      }
+      if (st == 0) {  // per-node guards: first node in sequence wins (bad covers the pair in node order)
+        if (bad) st = bad;
+        else if (isnan(kk.x) || (i + 1 < nint && isnan(kk.y))) st = LGAR_ST_NAN;
+      }
+    }
+#endif
     q->a[lane] = fabs(geff / s.ksat);
     q->st[lane] = st;
   }

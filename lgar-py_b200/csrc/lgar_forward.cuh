@@ -593,9 +593,13 @@ __global__ void __launch_bounds__(NT, (FM == 32) ? 1 : ((FM == 16) ? 2 : ((FM ==
     if (item >= nitems) break;
     const int chunk = (int)(item / K.ntiles);
     const int tile = (int)(item % K.ntiles);
-    const int b = tile * 32 + lane;
-    const bool valid = (size_t)b < B;
-    const int bb = valid ? b : (int)B - 1;  // clamp for loads; results of invalid lanes are never stored
+    // slot = position in the tile grid (state / checkpoint records); b = column of the ensemble this lane works on
+    // (lgar_problem.column_order: work-balanced placement; identity when NULL)
+    const int slot_c = tile * 32 + lane;
+    const bool valid = (size_t)slot_c < B;
+    const int slot_cc = valid ? slot_c : (int)B - 1;  // clamp for loads; results of invalid lanes are never stored
+    const int b = p.column_order ? __ldg(p.column_order + slot_cc) : slot_cc;
+    const int bb = b;
 
     // wait for the previous chunk of this tile (acquire): done[tile] = forcing rows completed (absolute row index)
     const int t0 = K.t_begin + chunk * K.chunk_steps;
@@ -616,7 +620,7 @@ __global__ void __launch_bounds__(NT, (FM == 32) ? 1 : ((FM == 16) ? 2 : ((FM ==
     load_params(K, bb, T);
     const int slot_in = K.keep_ckpt ? chunk : 0;
     if (chunk == 0 && p.resume) {
-      load_state(K, 0, bb, T);  // continue from the state the previous launch left in the workspace
+      load_state(K, 0, slot_cc, T);  // continue from the state the previous launch left in the workspace
       if (T.crash_step >= 0) T.crash_step = -2 - T.crash_step;  // crashed in an earlier call
     } else if (chunk == 0) {
       T.ctx.st = 0;
@@ -624,9 +628,9 @@ __global__ void __launch_bounds__(NT, (FM == 32) ? 1 : ((FM == 16) ? 2 : ((FM ==
       init_column(T, __ldg(p.initial_psi + bb), p.use_closed_form_G != 0);
       if (T.ctx.st) T.crash_step = 0;
       if (valid && K.o.start_volume) K.o.start_volume[b] = T.col.ending_volume;
-      if (K.keep_ckpt && valid) save_state(K, 0, b, T);
+      if (K.keep_ckpt && valid) save_state(K, 0, slot_c, T);
     } else {
-      load_state(K, slot_in, bb, T);
+      load_state(K, slot_in, slot_cc, T);
     }
     precompute_psi_wp(T, p.wilting_point_psi);
     const int site = (p.site_index && valid) ? __ldg(p.site_index + b) : 0;
@@ -672,7 +676,7 @@ __global__ void __launch_bounds__(NT, (FM == 32) ? 1 : ((FM == 16) ? 2 : ((FM ==
 
     // publish the state for the next chunk of this tile (release)
     const int slot_out = K.keep_ckpt ? chunk + 1 : 0;
-    if (valid) save_state(K, slot_out, b, T);
+    if (valid) save_state(K, slot_out, slot_c, T);
     if (chunk == K.nchunks - 1 && valid) {
       if (K.o.sums) {
 #pragma unroll

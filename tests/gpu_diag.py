@@ -18,6 +18,8 @@ for B, T in shapes:
     ens = ColumnEnsemble(theta_r=we.theta_r, theta_e=we.theta_e, thickness=we.thickness, forcing=we.forcing,
                          site_index=we.site_index, max_fronts=int(os.environ.get("LGAR_DIAG_FM", "16")),
                          chunk_steps=int(os.environ.get("LGAR_DIAG_CHUNK", "64")))
+    if os.environ.get("LGAR_DIAG_BALANCE"):
+        ens.balance(we.ksat)
     torch.cuda.synchronize(); t0 = time.time()
     res, ws = forward_raw(ens, we.alpha, we.n, we.ksat, outputs=("runoff", "AET"), counters=True, tile_cycles=True)
     torch.cuda.synchronize(); dt = time.time() - t0
