@@ -167,7 +167,10 @@ typedef struct lgar_outputs {
    * 3 k_from_se, 4 se_from_h, 5 theta root-finder iterations, 6 column-mass iterations,
    * 7 sub-steps.  Used for the algorithmic FLOP count of the roofline.            */
   unsigned long long* counters; /* [16]: 0-7 work counters; 8-11 warp cycles in insert-water Geff, move
-                                   sweep, dry-depth Geff, calc_dzdt; 12 total warp cycles; 13-15 reserved   */
+                                   sweep, dry-depth Geff, calc_dzdt; 12 total warp cycles; 13-15 branch coverage:
+                                   dry-over-wet fixes (Layer.py:1055-1096), insert_water equality fall-through
+                                   (Layer.py:1509-1521), calc_bottom_sum_f_p with the free-drainage front in
+                                   layer >= 2 (Layer.py:1538-1555)                                          */
   /* diagnostics: SM cycles spent on each tile of 32 consecutive columns, summed over chunks     */
   unsigned long long* tile_cycles; /* [ceil(B/32)]                                              */
 } lgar_outputs;
@@ -200,6 +203,33 @@ int lgar_forward(const lgar_problem* p, const lgar_outputs* out, void* workspace
 int lgar_backward(const lgar_problem* p, const double* grad_per_step, uint32_t grad_mask,
                   const double* grad_sums, double* grad_alpha, double* grad_n, double* grad_ksat,
                   void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* lgar_backward with options.  Everything lgar_backward takes, plus:
+ *   reduce != 0     the parameters are SHARED by all columns (the reference's model: one alpha/n/ksat per layer,
+ *                   models/dpLGAR.py:50-57, trained over many columns / sites at once): grad_alpha/n/ksat are [L]
+ *                   arrays holding the SUM over columns, reduced inside the library in a fixed order (warp shuffle
+ *                   per tile, then a fixed-order pass over the tile partials): bit-reproducible, no atomics, and the
+ *                   all-reduce input of a data-parallel calibration step comes straight out of our kernels.
+ *                   Columns whose tape overflowed contribute 0 (see tape_overflow).
+ *   tape_overflow   [B] or NULL: 1 where a column's tape arena was exhausted -- its gradient is not available
+ *                   (per-column mode: NaN) and the caller must not step on it.
+ *   partials        [ceil(B/32)][3 L] doubles of scratch for reduce != 0.
+ *   counters        [8] or NULL, diagnostics summed over warps: 0 cycles in the taped recompute, 1 cycles in the
+ *                   reverse sweeps, 2 tape entries recorded (per lane), 3 sub-steps taped (per lane), 4 overflowed columns. */
+typedef struct lgar_gradients {
+  const double* grad_per_step;  /* [popcount(grad_mask)][T][B] dL/d(per-step outputs) or NULL                */
+  uint32_t grad_mask;
+  int32_t reduce;
+  const double* grad_sums;      /* [NOUT][B] dL/d(sums) or NULL                                              */
+  double* grad_alpha;           /* [L][B], or [L] with reduce                                                */
+  double* grad_n;
+  double* grad_ksat;
+  double* partials;
+  int32_t* tape_overflow;
+  unsigned long long* counters;
+} lgar_gradients;
+int lgar_backward_ex(const lgar_problem* p, const lgar_gradients* g, void* workspace_dev, size_t workspace_bytes,
+                     void* stream);
 
 /* Convenience for non-CUDA hosts: same as lgar_forward but every pointer in `p` and `out` is a
  * HOST pointer; the library allocates device memory, copies in, runs, copies out, synchronises. */

@@ -20,7 +20,7 @@ OUT_NAMES = ("runoff", "percolation", "AET", "infiltration", "ending_volume", "p
 STATUS_NAMES = ("OK", "NEG_POW", "NAN", "THETA_ORDER", "BOTTOM_REACHED", "NULL_NEIGHBOUR",
                 "FRONT_OVERFLOW", "ITER_CAP", "INDEX_ERROR")
 EXPORTS = ("lgar_abi_version", "lgar_device_check", "lgar_last_error_string", "lgar_workspace_bytes",
-           "lgar_forward", "lgar_backward", "lgar_forward_host", "lgar_measure_fp64_flops")
+           "lgar_forward", "lgar_backward", "lgar_backward_ex", "lgar_forward_host", "lgar_measure_fp64_flops")
 
 _dp = C.c_void_p  # device or host pointer, passed as an integer address
 
@@ -47,6 +47,14 @@ class Outputs(C.Structure):
         ("sums", _dp), ("start_volume", _dp), ("status", _dp), ("crash_step", _dp),
         ("num_fronts", _dp), ("fronts", _dp), ("front_layer", _dp), ("front_to_bottom", _dp),
         ("counters", _dp), ("tile_cycles", _dp),
+    ]
+
+
+class Gradients(C.Structure):
+    _fields_ = [
+        ("grad_per_step", _dp), ("grad_mask", C.c_uint32), ("reduce", C.c_int32), ("grad_sums", _dp),
+        ("grad_alpha", _dp), ("grad_n", _dp), ("grad_ksat", _dp), ("partials", _dp), ("tape_overflow", _dp),
+        ("counters", _dp),
     ]
 
 
@@ -77,6 +85,8 @@ def lib():
         L.lgar_backward.restype = C.c_int
         L.lgar_backward.argtypes = [C.POINTER(Problem), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.lgar_backward_ex.restype = C.c_int
+        L.lgar_backward_ex.argtypes = [C.POINTER(Problem), C.POINTER(Gradients), C.c_void_p, C.c_size_t, C.c_void_p]
         L.lgar_forward_host.restype = C.c_int
         L.lgar_forward_host.argtypes = [C.POINTER(Problem), C.POINTER(Outputs)]
         L.lgar_measure_fp64_flops.restype = C.c_double

@@ -194,16 +194,27 @@ class DifferentiableLGAR:
     def train_one_epoch(self):
         """One pass over the record(s): one forward launch, mass-balance report, then `validate()`."""
         self.optimizer.zero_grad()
-        out = self.model.forward_record(self.x if self.x.shape[0] > 1 else self.x[0], outputs=self.OUTPUTS)
+        out = self.model.forward_record(self.x if self.x.shape[0] > 1 else self.x[0], outputs=self.OUTPUTS,
+                                        on_status="ignore")
         st = out.get("status")
         keep = None
-        if st is not None and bool((st != 0).any()):  # the reference raises out of model(x) (SURVEY Q9-Q11)
+        failed = st is not None and bool((st != 0).any())
+        msg = ""
+        if failed:
             from ._capi import STATUS_NAMES
+            from .model import CAPACITY_STATUSES
             first = (st.reshape(-1) != 0).nonzero()[0, 0]
             bad, step = int(st.reshape(-1)[first]), int(out["crash_step"].reshape(-1)[first])
-            msg = f"LGAR column status {STATUS_NAMES[bad]} at forcing step {step} (the reference raises here)"
-            if self.on_column_error == "raise":
-                raise RuntimeError(msg)
+            if bad in CAPACITY_STATUSES:  # a limit of this library, not a reference state (its front lists are unbounded)
+                msg = (f"LGAR column status {STATUS_NAMES[bad]} at forcing step {step}: a capacity limit of the CUDA library "
+                       "(16 wetting fronts per column in the differentiable path / 1e6 root-finder iterations), not a "
+                       "reference exception; mask the site (on_column_error='mask') or rerun it forward-only with max_fronts=32")
+            else:
+                msg = f"LGAR column status {STATUS_NAMES[bad]} at forcing step {step} (the reference raises here)"
+        if self.on_column_error == "raise" and self._any_rank(failed):
+            # every rank leaves together: a lone raise would leave the others waiting in the gradient all-reduce
+            raise RuntimeError(msg or "LGAR column failure on another rank")
+        if failed:
             keep = (st.reshape(-1) == 0)
             log.warning(f"{int((~keep).sum())} of {keep.numel()} sites left out of this epoch: {msg}")
         self._report_mass(out)
@@ -216,14 +227,20 @@ class DifferentiableLGAR:
             y_hat, y_t = y_hat[keep], y_t[keep]
         self.y_hat = y_hat[:, self.warmup:]
         self.y_t = y_t[:, self.warmup:]
+        self._no_sites = keep is not None and int(keep.sum()) == 0
         self.validate()
 
     def validate(self) -> None:
         """Loss = MSE(y_hat, y_t) + RangeBoundLoss(params); backward through the reverse-mode kernel; Adam step
         (agents/DifferentiableLGAR.py:136-171).  With several ranks the loss and gradients are averaged first."""
-        nse = calculate_nse(self.y_hat.detach().cpu().numpy().ravel(), self.y_t.cpu().numpy().ravel())
+        if getattr(self, "_no_sites", False):
+            # every site of this rank failed: contribute a zero loss and zero gradients (the collective still runs)
+            nse = float("nan")
+            loss_mse = self.y_hat.sum() * 0.0
+        else:
+            nse = calculate_nse(self.y_hat.detach().cpu().numpy().ravel(), self.y_t.cpu().numpy().ravel())
+            loss_mse = self.criterion(self.y_hat, self.y_t)
         log.info(f"trained NSE: {nse:.4}")
-        loss_mse = self.criterion(self.y_hat, self.y_t)
         params = [self.model.alpha, self.model.n, self.model.ksat, self.model.ponded_depth_max]
         bound_loss = self.range_bound_loss(params).to(loss_mse.device)
         loss = loss_mse + bound_loss
@@ -233,10 +250,22 @@ class DifferentiableLGAR:
         log.info(f"Back prop took : {(end - start):.6f} seconds")
         loss_val = self._allreduce_mean(loss.detach())
         log.info(f"Loss: {loss_val}")
+        # never step on a broken gradient: an exhausted tape arena (ColumnEnsemble.last_tape_overflow) or a non-finite
+        # entry would poison the parameters and Adam's moments for good
+        grads = [p.grad for p in self.model.parameters() if p.grad is not None]
+        finite = all(bool(torch.isfinite(g).all()) for g in grads)
+        ens = getattr(self.model, "last_ensemble", None)
+        overflowed = ens.check_tape_overflow(raise_error=False) if ens is not None else 0
+        if self._any_rank((not finite) or overflowed > 0):
+            self.optimizer.zero_grad()
+            raise RuntimeError(f"gradient not usable (finite: {finite}, columns with an exhausted tape arena: {overflowed}); "
+                               "the optimiser step was skipped")
         self.optimizer.step()
         self.history.append((self.current_epoch, float(loss_val), nse))
 
     def save_checkpoint(self, file_name="checkpoint.pth.tar", is_best=0):
+        if dist.is_available() and dist.is_initialized() and dist.get_rank(self.group) != 0:
+            return  # the ranks hold identical parameters: rank 0 writes
         state = {"epoch": self.current_epoch, "model": self.model.state_dict(), "optimizer": self.optimizer.state_dict(),
                  "history": list(self.history)}
         tmp = file_name + ".tmp"
@@ -246,7 +275,7 @@ class DifferentiableLGAR:
             torch.save(state, os.path.join(os.path.dirname(file_name) or ".", "model_best.pth.tar"))
 
     def load_checkpoint(self, file_name):
-        state = torch.load(file_name, map_location="cpu", weights_only=False)
+        state = torch.load(file_name, map_location="cpu", weights_only=True)
         self.model.load_state_dict(state["model"])
         self.optimizer.load_state_dict(state["optimizer"])
         self.current_epoch = int(state["epoch"])
@@ -257,6 +286,17 @@ class DifferentiableLGAR:
         self.save_checkpoint()
 
     # ---- helpers ----------------------------------------------------------------------------
+    def _any_rank(self, flag: bool) -> bool:
+        """Logical OR of a host flag over the ranks (so that all of them raise, or none)."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return bool(flag)
+        dev = next(self.model.parameters()).device if dist.get_backend(self.group) == "nccl" else torch.device("cpu")
+        if dev.type != "cuda" and dist.get_backend(self.group) == "nccl":
+            dev = torch.device("cuda", torch.cuda.current_device())
+        t = torch.tensor([1.0 if flag else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return bool(t.item() > 0)
+
     def _allreduce_mean(self, loss):
         """Average the loss and the parameter gradients over the ranks with ONE collective."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:

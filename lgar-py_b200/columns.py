@@ -54,10 +54,13 @@ class ColumnEnsemble:
     use_closed_form_G: bool = False  # cfg.data.use_closed_form_G (green_ampt.py:85-98)
     giuh_ordinates: Sequence[float] = (0.06, 0.51, 0.28, 0.12, 0.03)
     max_fronts: int = 16
-    chunk_steps: int = 64
+    chunk_steps: int = 0             # forcing steps per scheduling / checkpoint chunk (0 = library default: 64 sub-steps)
     iter_cap: int = 0
     resume: bool = False             # continue from the state left in the workspace (see lgar_b200.h)
     column_order: Optional[torch.Tensor] = None  # [B] int32 permutation: placement of columns on warps (lgar_b200.h)
+    reverse_counters: bool = False   # collect the reverse kernel's diagnostics counters (lgar_gradients.counters)
+    last_tape_overflow: Optional[torch.Tensor] = field(default=None, repr=False)   # [B] int32 after a backward pass
+    last_reverse_counters: Optional[torch.Tensor] = field(default=None, repr=False)
     device: object = "cuda"
     _keep: list = field(default_factory=list, repr=False)
 
@@ -112,6 +115,17 @@ class ColumnEnsemble:
         p.site_index = self.site_index.data_ptr() if self.site_index is not None else None
         p.column_order = self.column_order.data_ptr() if self.column_order is not None else None
         return p
+
+    def check_tape_overflow(self, raise_error=True) -> int:
+        """Number of columns whose reverse-pass tape arena was exhausted in the last backward pass (synchronises).
+        Their per-column gradients are NaN and the shared-parameter sums leave them out: do not step on them."""
+        ov = self.last_tape_overflow
+        cnt = int(ov.sum()) if ov is not None else 0
+        if cnt and raise_error:
+            raise _capi.LGARLibraryError(
+                f"{cnt} column(s) exhausted the tape arena of the reverse pass: their gradients are not available "
+                "(use a smaller chunk_steps, or mask these columns: ColumnEnsemble.last_tape_overflow)")
+        return cnt
 
     def balance(self, ksat) -> "ColumnEnsemble":
         """Place columns of similar cost on the same warp.  A warp advances its 32 columns in lock step, so its time per
@@ -270,7 +284,9 @@ def forward_raw(ens: ColumnEnsemble, alpha, n, ksat, outputs=("runoff", "percola
 
 
 class _LGARFunction(torch.autograd.Function):
-    """autograd bridge: forward = lgar_forward (stores chunk checkpoints), backward = lgar_backward."""
+    """autograd bridge: forward = lgar_forward (stores chunk checkpoints), backward = lgar_backward_ex.
+    Parameters given as `[L]` vectors are SHARED by all columns: their gradient (the sum over columns) is reduced
+    inside the library in a fixed order (no torch reduction kernel, bit-reproducible)."""
 
     @staticmethod
     def forward(ctx, alpha, n, ksat, ens: ColumnEnsemble, mask: int):
@@ -293,26 +309,45 @@ class _LGARFunction(torch.autograd.Function):
         dev = ens.device
         Lr, B = ens.num_layers, ens.num_columns
         p = ens.problem(alpha, n, ksat)
-        ga = torch.zeros((Lr, B), dtype=F64, device=dev)
+        sa, sn, sk = ctx.in_shapes
+        shared = len(sa) == 1 and len(sn) == 1 and len(sk) == 1
+        g = _capi.Gradients()
+        gshape = (Lr,) if shared else (Lr, B)
+        ga = torch.zeros(gshape, dtype=F64, device=dev)
         gn = torch.zeros_like(ga)
         gk = torch.zeros_like(ga)
         gps = g_per_step.contiguous() if (g_per_step is not None and g_per_step.numel()) else None
         gs = g_sums.contiguous() if g_sums is not None else None
+        overflow = torch.empty(B, dtype=torch.int32, device=dev)
+        g.grad_per_step = gps.data_ptr() if gps is not None else None
+        g.grad_mask = ctx.mask
+        g.grad_sums = gs.data_ptr() if gs is not None else None
+        g.grad_alpha, g.grad_n, g.grad_ksat = ga.data_ptr(), gn.data_ptr(), gk.data_ptr()
+        g.tape_overflow = overflow.data_ptr()
+        partials = None
+        if shared:
+            partials = torch.empty(((B + 31) // 32, 3 * _capi.MAX_LAYERS), dtype=F64, device=dev)
+            g.reduce, g.partials = 1, partials.data_ptr()
+        counters = None
+        if ens.reverse_counters:
+            counters = torch.zeros(8, dtype=torch.int64, device=dev)
+            g.counters = counters.data_ptr()
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
-            rc = L_.lgar_backward(C.byref(p), gps.data_ptr() if gps is not None else None, ctx.mask,
-                                  gs.data_ptr() if gs is not None else None, ga.data_ptr(), gn.data_ptr(),
-                                  gk.data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(), C.c_void_p(stream))
-        _capi.check(rc, "lgar_backward")
+            rc = L_.lgar_backward_ex(C.byref(p), C.byref(g), ctx.ws.data_ptr(), ctx.ws.numel(), C.c_void_p(stream))
+        _capi.check(rc, "lgar_backward_ex")
+        # the caller decides what to do with columns whose tape arena was exhausted (their per-column gradient is NaN;
+        # shared-parameter sums leave them out): see ColumnEnsemble.check_tape_overflow()
+        ens.last_tape_overflow = overflow
+        ens.last_reverse_counters = counters
 
-        def shape_back(g, shp):
-            return g.sum(dim=1) if len(shp) == 1 else g
-        sa, sn, sk = ctx.in_shapes
+        def shape_back(gr, shp):
+            return gr.sum(dim=1) if (len(shp) == 1 and gr.dim() == 2) else gr
         return shape_back(ga, sa), shape_back(gn, sn), shape_back(gk, sk), None, None
 
 
 def lgar_columns(alpha, n, ksat, ens: ColumnEnsemble, outputs=("runoff", "percolation")):
-    """Differentiable batched run.  alpha/n/ksat: `[L,B]` (per column) or `[L]` (shared).
+    """Differentiable batched run.  alpha/n/ksat: `[L,B]` (per column) or `[L]` (shared by all columns).
     Returns a dict: every requested output as `[T,B]`, plus `sums[NOUT,B]`, `start_volume[B]`,
     `status[B]`, `crash_step[B]`."""
     mask = output_mask(outputs)
@@ -320,10 +355,11 @@ def lgar_columns(alpha, n, ksat, ens: ColumnEnsemble, outputs=("runoff", "percol
     a = torch.as_tensor(alpha, dtype=F64).to(dev)
     nn_ = torch.as_tensor(n, dtype=F64).to(dev)
     k = torch.as_tensor(ksat, dtype=F64).to(dev)
-    ae = a if a.dim() == 2 else a.unsqueeze(1).expand(ens.num_layers, ens.num_columns)
-    ne = nn_ if nn_.dim() == 2 else nn_.unsqueeze(1).expand(ens.num_layers, ens.num_columns)
-    ke = k if k.dim() == 2 else k.unsqueeze(1).expand(ens.num_layers, ens.num_columns)
-    per_step, sums, sv, st, cs = _LGARFunction.apply(ae.contiguous(), ne.contiguous(), ke.contiguous(), ens, mask)
+    if not (a.dim() == 1 and nn_.dim() == 1 and k.dim() == 1):  # mixed: expand the shared ones (autograd sums them)
+        a = a if a.dim() == 2 else a.unsqueeze(1).expand(ens.num_layers, ens.num_columns)
+        nn_ = nn_ if nn_.dim() == 2 else nn_.unsqueeze(1).expand(ens.num_layers, ens.num_columns)
+        k = k if k.dim() == 2 else k.unsqueeze(1).expand(ens.num_layers, ens.num_columns)
+    per_step, sums, sv, st, cs = _LGARFunction.apply(a.contiguous(), nn_.contiguous(), k.contiguous(), ens, mask)
     out = {name: per_step[bin(mask & ((1 << OUT_NAMES.index(name)) - 1)).count("1")] for name in outputs}
     out.update(sums=sums, start_volume=sv, status=st, crash_step=cs)
     return out

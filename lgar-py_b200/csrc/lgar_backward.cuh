@@ -67,7 +67,28 @@ struct BParams {
   int32_t arena_cap;            // tape entries per lane for one chunk
   int32_t step_cap;             // max entries of one sub-step (ids are 16 bit)
   int32_t* tape_overflow;       // [B] set to 1 if a column's tape overflowed (gradient invalid)
+  int32_t reduce;               // 1: shared parameters -- per-tile sums into `partials`, no per-column gradients
+  double* partials;             // [ntiles][NPAR_IDS]
+  unsigned long long* counters; // [8] diagnostics (lgar_gradients.counters)
 };
+
+// second stage of the shared-parameter reduction: block q sums partials[.][q] over the tiles in a fixed order
+// (lane j takes tiles j, j+32, ... sequentially, then a butterfly over the 32 lane sums)
+__global__ void lgar_reduce_tile_partials(const double* partials, int ntiles, int L, double* grad_alpha, double* grad_n,
+                                          double* grad_ksat) {
+  const int q = blockIdx.x;  // 3 l + {0: alpha, 1: n, 2: ksat}
+  double s = 0.0;
+  for (int t = threadIdx.x; t < ntiles; t += 32) s += partials[(size_t)t * NPAR_IDS + q];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if (threadIdx.x == 0) {
+    const int l = q / 3;
+    if (l < L) {
+      double* out = (q % 3 == 0) ? grad_alpha : ((q % 3 == 1) ? grad_n : grad_ksat);
+      out[l] = s;
+    }
+  }
+}
 
 __host__ inline size_t backward_meta_bytes(int FM) {
   return FM == 16 ? sizeof(StepMeta<16>) : (FM == 12 ? sizeof(StepMeta<12>) : sizeof(StepMeta<8>));
@@ -82,7 +103,7 @@ __host__ inline size_t backward_scratch_bytes(int S, int FM, int chunk, int slot
 
 // GM = 0: trapezoid Geff only (closed-form branch compiled out of the taped sub-step); GM = 2: run-time switch
 template <int FM, int GM>
-__global__ void __launch_bounds__(NT) lgar_backward_kernel(const BParams P) {
+__global__ void __launch_bounds__(NT, 2) lgar_backward_kernel(const BParams P) {  // 2 CTAs per SM: up to 255 registers
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sm_fields = reinterpret_cast<double*>(smem_raw);                       // [5*FM][NT]
   double* sm_nodes = sm_fields + 5 * FM * NT;                                    // [WARPS][NODEBUF_TAPED]
@@ -146,8 +167,10 @@ __global__ void __launch_bounds__(NT) lgar_backward_kernel(const BParams P) {
 #pragma unroll
     for (int q = 0; q < NPAR_IDS; q++) gpar[q] = 0.0;
     bool overflow = false;
+    unsigned long long cyc_fwd = 0, cyc_rev = 0, n_entries = 0, n_sub = 0;
 
     for (int chunk = K.nchunks - 1; chunk >= 0; chunk--) {
+      const long long clk_a = clock64();
       const int t0 = chunk * K.chunk_steps;
       const int t1 = min(Tn, t0 + K.chunk_steps);
       // ---- forward through the chunk ON THE TAPE, from the checkpoint the forward kernel stored
@@ -181,6 +204,10 @@ __global__ void __launch_bounds__(NT) lgar_backward_kernel(const BParams P) {
           __syncwarp();
           if (tc.n > tc.cap) overflow = true;
           const int ne = min(tc.n, tc.cap);
+          if (alive) {
+            n_entries += (unsigned long long)ne;
+            n_sub++;
+          }
           StepMeta<FM>& M = metas[(size_t)j * 32];
           M.n_entries = ne;
           M.n_fronts = C.n;
@@ -197,6 +224,8 @@ __global__ void __launch_bounds__(NT) lgar_backward_kernel(const BParams P) {
         }
       }
       __syncwarp();
+      const long long clk_b = clock64();
+      cyc_fwd += (unsigned long long)(clk_b - clk_a);
       // ---- reverse sweep over the sub-steps of the chunk
       for (int t = t1 - 1; t >= t0; t--) {
         for (int sc = S - 1; sc >= 0; sc--) {
@@ -246,6 +275,7 @@ __global__ void __launch_bounds__(NT) lgar_backward_kernel(const BParams P) {
         }
       }
       __syncwarp();
+      cyc_rev += (unsigned long long)(clock64() - clk_b);
     }
     // ---- the initial state depends on the parameters: theta_init = theta_l(psi_init), K_init
     //      (data/utils.py:82-84, WettingFront.py:38-48); ending_volume(0) = mass_balance()
@@ -282,14 +312,35 @@ __global__ void __launch_bounds__(NT) lgar_backward_kernel(const BParams P) {
         for (int q = 0; q < NPAR_IDS; q++) gpar[q] += adj[(size_t)q * 32];
       }
     }
-    if (valid) {
+    if (P.reduce) {
+      // shared parameters: sum over the 32 columns of the tile in a fixed (butterfly) order; overflowed and
+      // out-of-range lanes contribute 0
+#pragma unroll
+      for (int q = 0; q < NPAR_IDS; q++) {
+        double v = (valid && !overflow) ? gpar[q] : 0.0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if (lane == 0) P.partials[(size_t)tile * NPAR_IDS + q] = v;
+      }
+    } else if (valid) {
       const double qnan = __longlong_as_double(0x7ff8000000000000LL);
       for (int l = 0; l < p.num_layers; l++) {
         P.grad_alpha[(size_t)l * B + b] = overflow ? qnan : gpar[3 * l];
         P.grad_n[(size_t)l * B + b] = overflow ? qnan : gpar[3 * l + 1];
         P.grad_ksat[(size_t)l * B + b] = overflow ? qnan : gpar[3 * l + 2];
       }
-      if (P.tape_overflow) P.tape_overflow[b] = overflow ? 1 : 0;
+    }
+    if (valid && P.tape_overflow) P.tape_overflow[b] = overflow ? 1 : 0;
+    if (P.counters) {
+      if (lane == 0) {
+        atomicAdd(P.counters + 0, cyc_fwd);
+        atomicAdd(P.counters + 1, cyc_rev);
+      }
+      if (valid) {
+        atomicAdd(P.counters + 2, n_entries);
+        atomicAdd(P.counters + 3, n_sub);
+        if (overflow) atomicAdd(P.counters + 4, 1ULL);
+      }
     }
     __syncwarp();
   }

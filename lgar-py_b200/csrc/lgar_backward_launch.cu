@@ -52,6 +52,11 @@ static int launch_backward(BParams& P, int S, int chunk, int slots, int arena_ca
   BW_TRY(cudaMemsetAsync(P.next_tile, 0, 64, st));
   kern<<<(unsigned)grid, NT, smem, st>>>(P);
   BW_TRY(cudaGetLastError());
+  if (P.reduce) {
+    lgar_reduce_tile_partials<<<NPAR_IDS, 32, 0, st>>>(P.partials, P.K.ntiles, P.K.p.num_layers, P.grad_alpha, P.grad_n,
+                                                      P.grad_ksat);
+    BW_TRY(cudaGetLastError());
+  }
   return 0;
 }
 

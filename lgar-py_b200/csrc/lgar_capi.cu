@@ -49,7 +49,9 @@ int shape_of(const lgar_problem* p, Shape& s) {
   s.FM = p->max_fronts == 0 ? 16 : p->max_fronts;
   if (s.FM != 8 && s.FM != 12 && s.FM != 16 && s.FM != 32)
     return fail(LGAR_E_INVALID, "max_fronts must be 8, 12, 16 or 32");
-  s.chunk = p->chunk_steps > 0 ? p->chunk_steps : 64;
+  // default: 64 sub-steps per scheduling / checkpoint chunk (64 forcing steps at S = 1, 5 at S = 12), which also
+  // bounds the tape arena of the reverse pass (one chunk of sub-steps per resident warp)
+  s.chunk = p->chunk_steps > 0 ? p->chunk_steps : (64 / s.S > 0 ? 64 / s.S : 1);
   s.t_begin = 0;
   s.t_end = s.T;
   if (p->step_begin != 0 || p->step_end != 0) {
@@ -89,13 +91,26 @@ int g_num_sms = 0;
 // reverse kernel: resident warps that own scratch (ring, tape, adjoints).  Sized without a device
 // query so that lgar_workspace_bytes works on a host without a GPU: <= 160 SMs, CTAs per SM bounded by
 // the shared-memory footprint of the value + id arrays.
-#define LGAR_TAPE_CAP 6144  /* + leaves must stay below 32768: ids are stored as 16 bit in shared memory */
-int backward_ctas_per_sm(const Shape& s) { return s.FM == 16 ? 2 : (s.FM == 12 ? 2 : 4); }
+#define LGAR_TAPE_CAP_MAX 6144  /* + leaves must stay below 32768: ids are stored as 16 bit in shared memory */
+// entries one sub-step may record.  LGAR_DEBUG_TAPE_CAP (environment, tests only) shrinks it to provoke the
+// overflow path: tests/test_gpu_gradients.py::test_tape_overflow_is_reported
+#include <cstdlib>
+static int tape_cap() {
+  const char* e = std::getenv("LGAR_DEBUG_TAPE_CAP");
+  if (e) {
+    const int v = std::atoi(e);
+    if (v >= 16 && v <= LGAR_TAPE_CAP_MAX) return v;
+  }
+  return LGAR_TAPE_CAP_MAX;
+}
+#define LGAR_TAPE_CAP tape_cap()
+int backward_ctas_per_sm(const Shape&) { return 2; }  // __launch_bounds__(NT, 2) of lgar_backward_kernel
 // tape arena of one chunk: average budget of LGAR_TAPE_AVG entries per sub-step (a sub-step may use up to
 // LGAR_TAPE_CAP); exhaustion flags the column (NaN gradient + tape_overflow)
 #define LGAR_TAPE_AVG 640
 int backward_arena_cap(const Shape& s) {
-  long long c = (long long)s.chunk * s.S * LGAR_TAPE_AVG;
+  long long c = (long long)s.chunk * s.S * LGAR_TAPE_AVG;  // chunk * S <= 512 (checked): fits an int
+  if (std::getenv("LGAR_DEBUG_TAPE_CAP")) c = LGAR_TAPE_CAP;
   if (c < LGAR_TAPE_CAP) c = LGAR_TAPE_CAP;
   return (int)c;
 }
@@ -222,6 +237,11 @@ int lgar_device_check(void) {
 size_t lgar_workspace_bytes(const lgar_problem* p, int with_grad) {
   Shape s;
   if (shape_of(p, s)) return 0;
+  if (with_grad && (long long)s.chunk * s.S > 512) {
+    fail(LGAR_E_INVALID, "chunk_steps * num_subcycles > 512: the tape arena of the reverse pass (one chunk of sub-steps per "
+                         "resident warp) would not fit; use chunk_steps = 0 (default) or a smaller value");
+    return 0;
+  }
   size_t total = carve(s, with_grad).total;
 #ifdef LGAR_WITH_BACKWARD
   if (with_grad)
@@ -241,6 +261,8 @@ int lgar_forward(const lgar_problem* p, const lgar_outputs* out, void* workspace
     return fail(LGAR_E_INVALID, "a required problem array is NULL");
   if (p->num_sites < 1) return fail(LGAR_E_INVALID, "num_sites < 1");
   if (p->resume && keep_checkpoints) return fail(LGAR_E_INVALID, "resume is not available with keep_checkpoints");
+  if (keep_checkpoints && (long long)s.chunk * s.S > 512)
+    return fail(LGAR_E_INVALID, "chunk_steps * num_subcycles > 512 with keep_checkpoints (reverse-pass tape arena)");
   if (s.FM == 32 && keep_checkpoints) return fail(LGAR_E_INVALID, "max_fronts = 32 is forward-only (no checkpoints)");
   if (keep_checkpoints && (s.t_begin != 0 || s.t_end != s.T))
     return fail(LGAR_E_INVALID, "a step window is forward-only (keep_checkpoints needs the whole record)");
@@ -301,13 +323,14 @@ int lgar_forward(const lgar_problem* p, const lgar_outputs* out, void* workspace
 }
 
 #ifdef LGAR_WITH_BACKWARD
-int lgar_backward(const lgar_problem* p, const double* grad_per_step, uint32_t grad_mask, const double* grad_sums,
-                  double* grad_alpha, double* grad_n, double* grad_ksat, void* workspace_dev, size_t workspace_bytes,
-                  void* stream) {
+int lgar_backward_ex(const lgar_problem* p, const lgar_gradients* g, void* workspace_dev, size_t workspace_bytes,
+                     void* stream) {
   Shape s;
   int rc = shape_of(p, s);
   if (rc) return rc;
-  if (!grad_alpha || !grad_n || !grad_ksat) return fail(LGAR_E_INVALID, "gradient output array is NULL");
+  if (!g) return fail(LGAR_E_INVALID, "gradients is NULL");
+  if (!g->grad_alpha || !g->grad_n || !g->grad_ksat) return fail(LGAR_E_INVALID, "gradient output array is NULL");
+  if (g->reduce && !g->partials) return fail(LGAR_E_INVALID, "reduce needs the partials scratch array");
   if (s.FM == 32) return fail(LGAR_E_INVALID, "max_fronts = 32 is forward-only");
   int dev = -1;
   if (cudaGetDevice(&dev) != cudaSuccess || dev != g_dev_checked) {
@@ -337,21 +360,43 @@ int lgar_backward(const lgar_problem* p, const double* grad_per_step, uint32_t g
   if (s.t_begin != 0 || s.t_end != s.T) return fail(LGAR_E_INVALID, "lgar_backward needs the whole record (no step window)");
   K.keep_ckpt = 1;
   K.iter_cap = p->iter_cap > 0 ? p->iter_cap : 1000000;
-  P.grad_per_step = grad_per_step;
-  P.grad_mask = grad_per_step ? grad_mask : 0;
-  P.grad_sums = grad_sums;
-  P.grad_alpha = grad_alpha;
-  P.grad_n = grad_n;
-  P.grad_ksat = grad_ksat;
+  P.grad_per_step = g->grad_per_step;
+  P.grad_mask = g->grad_per_step ? g->grad_mask : 0;
+  P.grad_sums = g->grad_sums;
+  P.grad_alpha = g->grad_alpha;
+  P.grad_n = g->grad_n;
+  P.grad_ksat = g->grad_ksat;
+  P.tape_overflow = g->tape_overflow;
+  P.reduce = g->reduce ? 1 : 0;
+  P.partials = g->partials;
+  P.counters = g->counters;
+  if (g->counters) CUDA_TRY(cudaMemsetAsync(g->counters, 0, 8 * sizeof(unsigned long long), st));
   unsigned char* scratch = w + c.total;
   return lgar_reverse_unit_launch(s.FM, &P, s.S, s.chunk, backward_slots(s), backward_arena_cap(s), LGAR_TAPE_CAP, g_num_sms,
                                   scratch, (void*)st, g_err, sizeof(g_err));
+}
+
+int lgar_backward(const lgar_problem* p, const double* grad_per_step, uint32_t grad_mask, const double* grad_sums,
+                  double* grad_alpha, double* grad_n, double* grad_ksat, void* workspace_dev, size_t workspace_bytes,
+                  void* stream) {
+  lgar_gradients g;
+  std::memset(&g, 0, sizeof(g));
+  g.grad_per_step = grad_per_step;
+  g.grad_mask = grad_mask;
+  g.grad_sums = grad_sums;
+  g.grad_alpha = grad_alpha;
+  g.grad_n = grad_n;
+  g.grad_ksat = grad_ksat;
+  return lgar_backward_ex(p, &g, workspace_dev, workspace_bytes, stream);
 }
 #endif
 
 #ifndef LGAR_WITH_BACKWARD
 int lgar_backward(const lgar_problem*, const double*, uint32_t, const double*, double*, double*, double*, void*,
                   size_t, void*) {
+  return fail(LGAR_E_INVALID, "library built without the reverse-mode kernel");
+}
+int lgar_backward_ex(const lgar_problem*, const lgar_gradients*, void*, size_t, void*) {
   return fail(LGAR_E_INVALID, "library built without the reverse-mode kernel");
 }
 #endif

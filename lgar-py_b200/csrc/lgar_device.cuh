@@ -50,6 +50,8 @@ struct Soil {  // one layer of one column: Layer.attributes + alpha/n/ksat (Laye
 struct Ctx {  // per-thread execution context
   int st;               // lgar_status, first error wins
   unsigned cnt[8];      // work counters
+  unsigned br[3];       // branch-coverage counters (counting kernels): 0 dry-over-wet fixes (A17), 1 insert_water equality
+                        // fall-through (Q8), 2 calc_bottom_sum_f_p with the free-drainage front in layer >= 2 (Q18)
   long long iter_cap;
   unsigned long long ph[4];  // phase timers (clock64 deltas; counting kernels only): 0 insert-water Geff, 1 move sweep +
                              // merge/cross/fix/update_psi, 2 dry-depth Geff + surficial front, 3 calc_dzdt (Geff per front)
@@ -109,6 +111,18 @@ __device__ __noinline__ double2 pow_x2(double x0, double y0, double x1, double y
 struct D4 {
   double a, b, c, d;
 };
+// two independent pows WITH their logs (a = x0^y0, b = log x0, c = x1^y1, d = log x1): the taped trapezoid nodes
+__device__ __noinline__ D4 pow_log_x2(double x0, double y0, double x1, double y1) {
+  const double xv[2] = {x0, x1}, yv[2] = {y0, y1};
+  double r[2], lg[2];
+  bool ok[2];
+  pow_core_v<2>(xv, yv, r, ok, lg);
+  if (!ok[0]) { r[0] = pow_slow(x0, y0); lg[0] = log(x0); }
+  if (!ok[1]) { r[1] = pow_slow(x1, y1); lg[1] = log(x1); }
+  D4 o;
+  o.a = r[0]; o.b = lg[0]; o.c = r[1]; o.d = lg[1];
+  return o;
+}
 
 // utils.py:12-32 safe_pow guards: NaN input or negative base raise ValueError
 __device__ __forceinline__ void guard_pow(double base, double e, Ctx& c) {
@@ -1013,37 +1027,35 @@ __device__ __noinline__ void geff_batch_eval(GeffQueue* q, const ST* soil, int L
   __syncwarp();
 }
 
-// Four trapezoid nodes with everything the reverse kernel needs (k_node_full, four chains interleaved): K and the
-// partials of K(Se(h; alpha, n, m); ksat, m) w.r.t. h, alpha, n, m; the logs are by-products of the pow cores.
-__device__ __forceinline__ void k_node_full_x4(const double (&h)[4], double alpha, double n, double m, double inv_m, double ksat,
-                                               double (&K)[4], double (&dk_h)[4], double (&dk_a)[4], double (&dk_n)[4],
-                                               double (&dk_m)[4], int (&bad)[4]) {
-  bool w[4], ok[4];
-  double x[4], y[4], ap[4], lx[4], u[4], um[4], lu[4], se[4], sp[4], lse[4], base[4], op[4], lb[4];
+// Two trapezoid nodes with everything the reverse kernel needs (k_node_full, two chains interleaved through the one
+// shared pow_log_x2 body): K and the partials of K(Se(h; alpha, n, m); ksat, m) w.r.t. h, alpha, n, m.
+struct NodeFull2 {
+  double K[2], dk_h[2], dk_a[2], dk_n[2], dk_m[2];
+  int bad[2];
+};
+__device__ __noinline__ NodeFull2 k_node_full_x2(double h0, double h1, double alpha, double n, double m, double inv_m,
+                                                 double ksat) {
+  NodeFull2 r;
+  const double h[2] = {h0, h1};
+  bool w[2];
+  double x[2], ap[2], lx[2], u[2], um[2], lu[2], se[2], sp[2], lse[2], base[2], op[2], lb[2];
 #pragma unroll
-  for (int e = 0; e < 4; e++) {
+  for (int e = 0; e < 2; e++) {
     w[e] = fabs(h[e]) < 1.0e-01;
     x[e] = w[e] ? 1.0 : alpha * h[e];
-    bad[e] = isnan(x[e]) ? LGAR_ST_NAN : (x[e] < 0.0 ? LGAR_ST_NEG_POW : 0);
-    y[e] = n;
+    r.bad[e] = isnan(x[e]) ? LGAR_ST_NAN : (x[e] < 0.0 ? LGAR_ST_NEG_POW : 0);
   }
-  pow_core_v<4>(x, y, ap, ok, lx);
+  D4 q = pow_log_x2(x[0], n, x[1], n);
+  ap[0] = q.a; lx[0] = q.b; ap[1] = q.c; lx[1] = q.d;
+  u[0] = 1.0 + ap[0];
+  u[1] = 1.0 + ap[1];
+  q = pow_log_x2(u[0], m, u[1], m);
+  um[0] = q.a; lu[0] = q.b; um[1] = q.c; lu[1] = q.d;
+  double dse_dh[2], dse_da[2], dse_dn[2], dse_dm[2];
 #pragma unroll
-  for (int e = 0; e < 4; e++) {
-    if (!ok[e]) { ap[e] = pow_slow(x[e], n); lx[e] = log(x[e]); }
-    u[e] = 1.0 + ap[e];
-    y[e] = m;
-  }
-  pow_core_v<4>(u, y, um, ok, lu);
-#pragma unroll
-  for (int e = 0; e < 4; e++) {
-    if (!ok[e]) { um[e] = pow_slow(u[e], m); lu[e] = log(u[e]); }
+  for (int e = 0; e < 2; e++) {
     se[e] = 1.0 / um[e];
-    if (!bad[e] && isnan(se[e])) bad[e] = LGAR_ST_NAN;
-  }
-  double dse_dh[4], dse_da[4], dse_dn[4], dse_dm[4];
-#pragma unroll
-  for (int e = 0; e < 4; e++) {
+    if (!r.bad[e] && isnan(se[e])) r.bad[e] = LGAR_ST_NAN;
     if (w[e]) {
       se[e] = 1.0;
       dse_dh[e] = dse_da[e] = dse_dn[e] = dse_dm[e] = 0.0;
@@ -1055,26 +1067,24 @@ __device__ __forceinline__ void k_node_full_x4(const double (&h)[4], double alph
       dse_dn[e] = (x[e] == 0.0) ? 0.0 : dse_du * ap[e] * lx[e];
       dse_dm[e] = -se[e] * lu[e];
     }
-    y[e] = inv_m;
   }
-  pow_core_v<4>(se, y, sp, ok, lse);
+  q = pow_log_x2(se[0], inv_m, se[1], inv_m);
+  sp[0] = q.a; lse[0] = q.b; sp[1] = q.c; lse[1] = q.d;
 #pragma unroll
-  for (int e = 0; e < 4; e++) {
-    if (!ok[e]) { sp[e] = pow_slow(se[e], inv_m); lse[e] = log(se[e]); }
+  for (int e = 0; e < 2; e++) {
     base[e] = 1.0 - sp[e];
     if (fabs(base[e]) <= 1e-8) base[e] = base[e] + 1e-12;
-    if (!bad[e]) bad[e] = isnan(base[e]) ? LGAR_ST_NAN : (base[e] < 0.0 ? LGAR_ST_NEG_POW : 0);
-    y[e] = m;
+    if (!r.bad[e]) r.bad[e] = isnan(base[e]) ? LGAR_ST_NAN : (base[e] < 0.0 ? LGAR_ST_NEG_POW : 0);
   }
-  pow_core_v<4>(base, y, op, ok, lb);
+  q = pow_log_x2(base[0], m, base[1], m);
+  op[0] = q.a; lb[0] = q.b; op[1] = q.c; lb[1] = q.d;
 #pragma unroll
-  for (int e = 0; e < 4; e++) {
-    if (!ok[e]) { op[e] = pow_slow(base[e], m); lb[e] = log(base[e]); }
+  for (int e = 0; e < 2; e++) {
     const double t = 1.0 - op[e];
-    if (!bad[e]) bad[e] = isnan(t) ? LGAR_ST_NAN : (t < 0.0 ? LGAR_ST_NEG_POW : 0);
+    if (!r.bad[e]) r.bad[e] = isnan(t) ? LGAR_ST_NAN : (t < 0.0 ? LGAR_ST_NEG_POW : 0);
     const double rs = sqrt(se[e]);
-    K[e] = ksat * rs * (t * t);
-    if (!bad[e] && isnan(K[e])) bad[e] = LGAR_ST_NAN;
+    r.K[e] = ksat * rs * (t * t);
+    if (!r.bad[e] && isnan(r.K[e])) r.bad[e] = LGAR_ST_NAN;
     // -dop/dse = op sp / (base se);  dop/dm = op ln(base) + op sp ln(se) / (base m)   (k_se_partials_core)
     const double sp_over = (se[e] == 0.0) ? 0.0 : sp[e] / se[e];
     const double ndop_dse = op[e] * sp_over / base[e];
@@ -1082,11 +1092,12 @@ __device__ __forceinline__ void k_node_full_x4(const double (&h)[4], double alph
     const double dop_dm = op[e] * lb[e] + op[e] * sp[e] * lnse / (base[e] * m);
     const double dk_se = ksat * ((rs == 0.0 ? 0.0 : t * t / (2.0 * rs)) + 2.0 * t * rs * ndop_dse);
     const double dkm = ksat * rs * 2.0 * t * (-dop_dm);
-    dk_h[e] = dk_se * dse_dh[e];
-    dk_a[e] = dk_se * dse_da[e];
-    dk_n[e] = dk_se * dse_dn[e];
-    dk_m[e] = dk_se * dse_dm[e] + dkm;
+    r.dk_h[e] = dk_se * dse_dh[e];
+    r.dk_a[e] = dk_se * dse_da[e];
+    r.dk_n[e] = dk_se * dse_dn[e];
+    r.dk_m[e] = dk_se * dse_dm[e] + dkm;
   }
+  return r;
 }
 
 // Taped pass: value (the forward kernel's bits) and the partials of Geff w.r.t. theta_1, theta_2, alpha, n, m of
@@ -1121,30 +1132,26 @@ __device__ __noinline__ void geff_batch_eval_taped(GeffQueue* q, const ST* soil,
     const double inv_nint = 1.0 / (double)nint;
     double geff = 0.0;
     double h2 = h_i + dh;
-    for (int i = 0; i < nint; i += 4) {
-      double h[4], kk[4], dk_h[4], dk_a[4], dk_n[4], dk_m[4];
-      int bad[4];
-      h[0] = h2;
-      h[1] = h[0] + dh;
-      h[2] = h[1] + dh;
-      h[3] = h[2] + dh;
-      h2 = h[3] + dh;
-      k_node_full_x4(h, s.alpha, s.n, s.m, s.inv_m, s.ksat, kk, dk_h, dk_a, dk_n, dk_m, bad);
+#pragma unroll 1
+    for (int i = 0; i < nint; i += 2) {
+      const double ha = h2, hb = ha + dh;
+      h2 = hb + dh;
+      const NodeFull2 nf = k_node_full_x2(ha, hb, s.alpha, s.n, s.m, s.inv_m, s.ksat);
 #pragma unroll
-      for (int e = 0; e < 4; e++) {
+      for (int e = 0; e < 2; e++) {
         const int node = i + e + 1;
         if (node <= nint) {
-          if (st == 0 && bad[e]) st = bad[e];
-          geff = geff + ((k1 + kk[e]) * half);
-          k1 = kk[e];
+          if (st == 0 && nf.bad[e]) st = nf.bad[e];
+          geff = geff + ((k1 + nf.K[e]) * half);
+          k1 = nf.K[e];
           const double wgt = (node == nint) ? 0.5 : 1.0;
           const double frac = (double)node * inv_nint;
-          S += wgt * kk[e];
-          Ahi += wgt * dk_h[e] * (1.0 - frac);
-          Ahf += wgt * dk_h[e] * frac;
-          Ca += wgt * dk_a[e];
-          Cn += wgt * dk_n[e];
-          Cm += wgt * dk_m[e];
+          S += wgt * nf.K[e];
+          Ahi += wgt * nf.dk_h[e] * (1.0 - frac);
+          Ahf += wgt * nf.dk_h[e] * frac;
+          Ca += wgt * nf.dk_a[e];
+          Cn += wgt * nf.dk_n[e];
+          Cm += wgt * nf.dk_m[e];
         }
       }
     }
@@ -1983,6 +1990,7 @@ struct Column {
         if (!has_next) continue;
         const int nx = i + 1;
         if (f(F_THETA, i) <= f(F_THETA, nx) && lay(i) == lay(nx)) {
+          c.br[0]++;
           const R mass_before = mass_balance();
           const int popped_layer = lay(i);
           erase_at(i, l);  // the former next front now sits at flat index i

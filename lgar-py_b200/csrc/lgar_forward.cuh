@@ -190,7 +190,10 @@ __device__ void substep(Tile<FM, R>& T, bool act, double precip_rate, double pet
         // unsaturated calc_bottom_sum for the remaining upper layers
         const R k0 = C.soil[0].ksatR() * K.p.frozen_factor;
         bottom_sum = bottom_sum + ((C.cum[0] - 0.0) / k0);
-        if (1 != lfp) bottom_sum = C.calc_bottom_sum(1, bottom_sum, C.g(F_PSI, fd), lfp, c);
+        if (1 != lfp) {
+          c.br[2]++;
+          bottom_sum = C.calc_bottom_sum(1, bottom_sum, C.g(F_PSI, fd), lfp, c);
+        }
         f_p = (fd_depth / bottom_sum) + ((geff + h_p) * fd_ksat / fd_depth);
       }
       const R ponded_temp = clamp_min_(ponded_depth_sub - f_p * dt - 0.0, 0.0);
@@ -202,6 +205,8 @@ __device__ void substep(Tile<FM, R>& T, bool act, double precip_rate, double pet
         } else if (ponded_temp > C.pdm) {
           ponded_depth_sub = R(C.pdm);
           infiltration_sub = fp_cm;
+        } else {
+          c.br[1]++;  // equality: neither branch of the reference runs (Q8)
         }
         runoff_sub = clamp_min_(ponded_temp - C.pdm, 0.0);
       } else {
@@ -616,6 +621,8 @@ __global__ void __launch_bounds__(NT, (FM == 32) ? 1 : ((FM == 16) ? 2 : ((FM ==
     for (int k = 0; k < 8; k++) T.ctx.cnt[k] = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) T.ctx.ph[k] = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) T.ctx.br[k] = 0;
     const long long clk0 = clock64();
     load_params(K, bb, T);
     const int slot_in = K.keep_ckpt ? chunk : 0;
@@ -689,6 +696,9 @@ __global__ void __launch_bounds__(NT, (FM == 32) ? 1 : ((FM == 16) ? 2 : ((FM ==
 #pragma unroll
       for (int k = 0; k < 8; k++)
         if (T.ctx.cnt[k]) atomicAdd(K.o.counters + k, (unsigned long long)T.ctx.cnt[k]);
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+        if (T.ctx.br[k]) atomicAdd(K.o.counters + 13 + k, (unsigned long long)T.ctx.br[k]);
       if (lane == 0) {  // phase timers of this warp (entries 8..11) and its total chunk time (12)
 #pragma unroll
         for (int k = 0; k < 4; k++) atomicAdd(K.o.counters + 8 + k, T.ctx.ph[k]);

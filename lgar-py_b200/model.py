@@ -41,6 +41,10 @@ KSAT_TABLE = (0.612, 0.3348, 0.504, 4.32, 26.64, 0.468, 0.54, 1.584, 1.836, 0.43
               0.45, 0.07, 0.45, 0.07, 0.02, 0.2)
 
 
+# statuses that are capacity limits of the CUDA library rather than exceptions of the reference
+CAPACITY_STATUSES = (STATUS_NAMES.index("FRONT_OVERFLOW"), STATUS_NAMES.index("ITER_CAP"))
+
+
 def _get(cfg, path, default=None):
     cur = cfg
     for key in path.split("."):
@@ -148,12 +152,27 @@ class dpLGAR(nn.Module):
         self.ending_volume = v["ending_volume"]
         return self.runoff, self.percolation
 
-    def forward_record(self, x, outputs=("runoff", "percolation")):
+    def forward_record(self, x, outputs=("runoff", "percolation"), on_status="raise"):
         """Whole record `x[T,2]` in one persistent launch, from the initial state; differentiable in alpha/n/ksat.
-        Returns a dict of `[T]` tensors (or `[T, columns]`)."""
+        Returns a dict of `[T]` tensors (or `[T, columns]`).  on_status: what to do when a column ends with a non-zero
+        status (its series are NaN from the crash step on): "raise" (default: the reference raises out of model(x)),
+        "warn" or "ignore" (the caller inspects out["status"] itself, like the agent does)."""
         a, n, k = self._params()
         ens = self._ensemble(torch.as_tensor(x, dtype=torch.float64))
+        self.last_ensemble = ens  # (the reverse pass leaves its tape-overflow flags there)
         out = lgar_columns(a, n, k, ens, outputs=outputs)
+        if on_status != "ignore":
+            st = out["status"]
+            if bool((st != 0).any()):
+                first = int((st != 0).nonzero()[0, 0])
+                code, step = int(st[first]), int(out["crash_step"][first])
+                kind = ("a capacity limit of the CUDA library, not a reference exception" if code in CAPACITY_STATUSES
+                        else "the reference raises here")
+                msg = f"LGAR column {first}: status {STATUS_NAMES[code]} at forcing step {step} ({kind})"
+                if on_status == "raise":
+                    raise RuntimeError(msg)
+                import warnings
+                warnings.warn(msg)
         if self.columns == 1:
             out = {key: (val[..., 0] if val.dim() >= 1 and val.shape[-1] == 1 else val) for key, val in out.items()}
         return out

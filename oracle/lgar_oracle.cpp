@@ -79,7 +79,9 @@ typedef struct {
 // ------------------------------------------------------------------------------------
 // scalar abstraction
 // ------------------------------------------------------------------------------------
-static thread_local long long g_cnt[8];  // 0 geff, 1 theta_from_h, 2 h_from_se, 3 k_from_se, 4 se_from_h, 5 rootfind iters, 6 colmass iters
+static thread_local long long g_cnt[12];  // 0 geff, 1 theta_from_h, 2 h_from_se, 3 k_from_se, 4 se_from_h, 5 rootfind iters, 6 colmass iters,
+                                         // 7 unused; branch coverage: 8 dry-over-wet fixes (A17), 9 insert_water equality (Q8),
+                                         // 10 calc_bottom_sum_f_p with the free-drainage front in layer >= 2 (Q18), 11 domain-boundary pops (A16)
 
 #ifndef LGAR_NT
 #define LGAR_NT 9
@@ -801,6 +803,7 @@ struct Column {
       if (e.n2n == nullptr) {
         if (val(e.cur->depth) > ly.cum) {
           if (!e.next) throw RefError{ST_NULL_NEIGHBOUR};
+          g_cnt[11]++;
           tmp = (e.cur->theta - e.next->theta) * (e.cur->depth - e.next->depth);
           e.next->theta = e.cur->theta;
           T se_k = se_from_theta(e.cur->theta, ly.s);
@@ -825,6 +828,7 @@ struct Column {
         bool theta_less = val(nb.cur->theta) <= val(nb.next->theta);
         bool same_layer = nb.cur->layer_num == nb.next->layer_num;
         if (theta_less && same_layer) {
+          g_cnt[8]++;
           T mass_before = mass_balance();
           Front<T>* popped = ly.wf[i];
           ly.wf.erase(ly.wf.begin() + i);
@@ -1007,7 +1011,10 @@ struct Column {
       T k0 = layers[0].s.ksat * cfg.frozen_factor;
       bottom_sum = bottom_sum + ((layers[0].cum - 0.0) / k0);
       if (L < 2) throw RefError{ST_NULL_NEIGHBOUR};
-      if (layers[1].l != fd->layer_num) bottom_sum = calc_bottom_sum(1, bottom_sum, fd);
+      if (layers[1].l != fd->layer_num) {
+        g_cnt[10]++;
+        bottom_sum = calc_bottom_sum(1, bottom_sum, fd);
+      }
       f_p = (fd->depth / bottom_sum) + ((geff + h_p) * fd_ksat / fd->depth);
     }
     (void)current_front;  // theta_e1 / layer_nums_equal guard can never fire (Q6)
@@ -1021,6 +1028,8 @@ struct Column {
       } else if (val(ponded_temp) > pdm) {
         ponded_depth = T(pdm);
         infiltration = fp_cm;
+      } else {
+        g_cnt[9]++;
       }
       runoff_out = clamp_min_(ponded_temp - pdm, 0.0);
     } else {

@@ -103,7 +103,7 @@ def forward(cfg: OracleCfg, forcing: np.ndarray, fronts: bool = True):
     ftb = np.zeros((T, FMAX), dtype=np.int8) if fronts else None
     nf = np.zeros(T, dtype=np.int32)
     crash = C.c_int32(-1)
-    cnt = np.zeros(8, dtype=np.int64)
+    cnt = np.zeros(12, dtype=np.int64)  # 0-6 work counters, 8-11 branch coverage (lgar_oracle.cpp g_cnt)
     st = lib().lgar_oracle_forward(
         C.byref(cfg), _p(forcing, C.c_double), C.c_int(T), _p(out, C.c_double), _p(fr, C.c_double),
         _p(fl, C.c_int8), _p(ftb, C.c_int8), _p(nf, C.c_int32), C.byref(crash), _p(cnt, C.c_longlong))

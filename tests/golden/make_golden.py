@@ -103,6 +103,18 @@ def cases():
         c[f"a16_col{col}"] = dict(ens=(col, T_))
     for col, T_ in ((10049, 60), (8074, 160)):
         c[f"null_col{col}"] = dict(ens=(col, T_))
+    # Q8: insert_water with ponded_depth_temp == ponded_depth_max EXACTLY falls through both branches (Layer.py:1509-1521).
+    # ponded_depth_max is set to the bits of the ponded water that phil_4500_400_pdm2 holds after its first ponding
+    # step (row 96): up to that step the state does not depend on ponded_depth_max, so ponded_depth_temp hits it.
+    c["phil_4500_400_pdm_eq"] = dict(forcing=(PHIL, 4500, 400), cfg=dict(ponded_depth_max=0.40456950118861856))
+    # frozen_factor != 1 (cfg.constants.frozen_factor): scales ksat at construction (dpLGAR.py:57), the K of a new
+    # surficial front (Layer.py:1411), the free-drainage ksat of insert_water (:1467) and calc_bottom_sum_f_p (:1545)
+    FF = dict(frozen_factor=0.7)
+    c["frozen_phil_4500_400"] = dict(forcing=(PHIL, 4500, 400), cfg=dict(**FF))
+    c["frozen_bush_5500_400_pdm2"] = dict(forcing=(BUSH, 5500, 400), cfg=dict(layer_soil_type=(15, 16, 17), ponded_depth_max=2.0, **FF))
+    c["frozen_ens_col8074"] = dict(ens=(8074, 160), cfg=dict(**FF))      # free-drainage front in layer 2 (Q18) with the factor
+    c["frozen_rand_phil_0"] = dict(forcing=(PHIL, 4500, 400), cfg=dict(**FF), alpha=al[8], n=nn[8], ksat=ks[8])
+    c["grad_frozen_phil_4550_150"] = dict(forcing=(PHIL, 4550, 150), grad=G, cfg=dict(**FF))
     # full-year known answers (config[0]); no per-step front dump to keep the files small
     c["phil_year"] = dict(forcing=(PHIL, 0, 8760), fronts=False)
     c["bush_year"] = dict(forcing=(BUSH, 0, 8760), cfg=dict(layer_soil_type=(15, 16, 17)),
@@ -122,7 +134,7 @@ def run_case(name):
         site = int(we.site_index[col])
         f = we.forcing[site, :T_].copy()
         spec = dict(spec, alpha=we.alpha[:, col], n=we.n[:, col], ksat=we.ksat[:, col],
-                    cfg=dict(layer_soil_type=(12, 13, 14) if site % 2 == 0 else (15, 16, 17)))
+                    cfg=dict(spec.get("cfg") or {}, layer_soil_type=(12, 13, 14) if site % 2 == 0 else (15, 16, 17)))
         path, start, count = f"workloads.synthetic_sites_ensemble(B=16000,T=2560,sites=128,rank=0)/site{site}/col{col}", 0, T_
     else:
         path, start, count = spec["forcing"]

@@ -39,7 +39,7 @@ class ToyModel(torch.nn.Module):
     def set_internal_states(self):
         self.resets += 1
 
-    def forward_record(self, x, outputs=("runoff",)):
+    def forward_record(self, x, outputs=("runoff",), on_status="raise"):
         x = torch.as_tensor(x, dtype=torch.float64)
         if x.dim() == 2:
             x = x[None]

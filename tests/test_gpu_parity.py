@@ -53,3 +53,56 @@ def test_cuda_full_year(name):
         ex = max_excess(r[k][:, 0], g[k])
         assert ex <= 1.0, f"{k}: exceeds tolerance by factor {ex:.3g}"
         np.testing.assert_array_equal(r[k][:, 0], r[k][:, 1])  # identical columns -> identical bits
+
+
+def test_goldens_enter_the_rare_branches_on_the_gpu():
+    """Same as tests/test_oracle_vs_golden.py::test_goldens_enter_the_rare_branches, counted by the CUDA kernel
+    (lgar_outputs.counters 6, 13, 14, 15): the parity above is only worth something where these are non-zero."""
+    from gpu_common import run_golden_on_gpu
+    tot = np.zeros(16, dtype=np.int64)
+    for name in CASES:
+        tot += run_golden_on_gpu(load_golden(name), copies=1)["counters"]
+    assert tot[6] > 0, "check_column_mass (A12) never iterated"
+    assert tot[13] > 0, "no dry-over-wet fix (A17)"
+    assert tot[14] > 0, "no insert_water equality fall-through (Q8)"
+    assert tot[15] > 0, "calc_bottom_sum_f_p never saw the free-drainage front in layer >= 2 (Q18)"
+
+
+@pytest.mark.parametrize("which", ["c4", "c3"])
+def test_full_year_random_columns_match_oracle(which):
+    """Where the bench lives: 64 random-parameter columns of the C4 shard / of the C3 Bushland ensemble over the whole
+    8760 h record against the CPU oracle: status, crash step and per-step front counts exact, the ten per-step fluxes
+    within 1e-9 relative + 1e-12 absolute."""
+    import torch
+    from lgar_b200 import workloads, ColumnEnsemble, forward_raw, OUT_NAMES
+    from oracle import lgar_oracle as O
+    B, T = 64, 8760
+    if which == "c4":
+        big = workloads.synthetic_sites_ensemble(B=125_000, T=T, sites=128, rank=0)
+    else:
+        big = workloads.bushland_ensemble(B=100_000, T=T, seed=0)
+    cols = np.random.default_rng(5).choice(big.num_columns, B, replace=False)
+    sl = lambda x: np.ascontiguousarray(x[:, cols])
+    ens = ColumnEnsemble(theta_r=sl(big.theta_r), theta_e=sl(big.theta_e), thickness=sl(big.thickness), forcing=big.forcing,
+                         site_index=big.site_index[cols])
+    res, _ = forward_raw(ens, sl(big.alpha), sl(big.n), sl(big.ksat), outputs=OUT_NAMES, num_fronts=True)
+    torch.cuda.synchronize()
+    status = res.status.cpu().numpy(); crash = res.crash_step.cpu().numpy(); nf = res.num_fronts.cpu().numpy()
+    series = res.per_step.cpu().numpy()   # [NOUT, T, B]
+    worst, n_ok = 0.0, 0
+    for j, b in enumerate(cols):
+        cfg = O.make_cfg(big.alpha[:, b], big.n[:, b], big.ksat[:, b], big.theta_r[:, b], big.theta_e[:, b],
+                         thickness=big.thickness[:, b], iter_cap=1_000_000)
+        r = O.forward(cfg, big.forcing[big.site_index[b]], fronts=False)
+        assert r["status"] == status[j], f"column {b}: status {status[j]} vs oracle {r['status']}"
+        n = T
+        if r["status"] != 0:
+            assert r["crash_step"] == crash[j], f"column {b}: crash step {crash[j]} vs oracle {r['crash_step']}"
+            n = r["crash_step"]
+        else:
+            n_ok += 1
+        np.testing.assert_array_equal(nf[:n, j], r["nfronts"][:n], err_msg=f"column {b}: front counts")
+        for k in range(len(OUT_NAMES)):
+            worst = max(worst, max_excess(series[k, :n, j], r["out"][:n, k]))
+    assert n_ok >= B // 2
+    assert worst <= 1.0, f"{which}: CUDA vs oracle exceeds 1e-9 rel + 1e-12 abs by factor {worst:.3g}"

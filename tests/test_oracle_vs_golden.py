@@ -88,3 +88,41 @@ def test_batch_runner_equals_single_runs():
         assert st[i] == r["status"]
         assert sums[i, 2] == pytest.approx(r["AET"].sum(), rel=1e-14)
         assert sums[i, 4] == r["ending_volume"][-1]
+
+
+def test_goldens_enter_the_rare_branches():
+    """The golden set must actually exercise the branches a port is most likely to get wrong: the saturated
+    free-drainage depth search (A12, check_column_mass), the dry-over-wet fix (A17), the equality fall-through of
+    insert_water (Q8), calc_bottom_sum_f_p with the free-drainage front in layer >= 2 (Q18) and the domain-boundary
+    pop (A16).  Counted by the oracle (g_cnt[6], [8..11]) over all forward goldens."""
+    tot = np.zeros(12, dtype=np.int64)
+    for name in ALL:
+        g = load_golden(name)
+        if "year" in name:
+            continue
+        tot += O.forward(O.cfg_from_golden(g), g["forcing"], fronts=False)["counters"]
+    assert tot[6] > 0, "check_column_mass never iterated"
+    assert tot[8] > 0 and tot[9] > 0 and tot[10] > 0 and tot[11] > 0, tot[8:].tolist()
+    # the frozen-factor goldens (frozen_factor = 0.7) hit Q18 with the factor applied (Layer.py:1467,1545)
+    g = load_golden("frozen_ens_col8074")
+    assert float(g["frozen_factor"]) == 0.7
+    assert O.forward(O.cfg_from_golden(g), g["forcing"], fronts=False)["counters"][10] > 0
+
+
+def test_batch_ex_crash_steps_and_tangent_sums():
+    names = ("rand_phil_1", "thin_crash")
+    g0 = load_golden("rand_phil_1")
+    cfgs = [O.cfg_from_golden(g0)]
+    r = O.forward_batch_ex(cfgs, g0["forcing"], nthreads=1, tangents=True)
+    one = O.forward_tangent(cfgs[0], g0["forcing"])
+    assert r["status"][0] == 0 and r["crash_step"][0] == -1
+    np.testing.assert_allclose(r["dsums"][0, 0], one["dout"][:, 0].sum(axis=0), rtol=1e-12, atol=1e-300)
+    np.testing.assert_array_equal(r["dsums"][0, 4], one["dout"][-1, 4])
+    gc = load_golden("thin_crash")
+    rc = O.forward_batch_ex([O.cfg_from_golden(gc)], gc["forcing"], nthreads=1)
+    assert rc["status"][0] != 0 and rc["crash_step"][0] == int(gc["crash_step"])
+    # per-column forcing records through `site`
+    f = np.stack([g0["forcing"][:40], g0["forcing"][100:140]])
+    two = O.forward_batch_ex([cfgs[0], cfgs[0]], f, site=[0, 1], nthreads=2)
+    a = O.forward(cfgs[0], f[1], fronts=False)
+    assert two["sums"][1, 2] == pytest.approx(a["AET"].sum(), rel=1e-14)

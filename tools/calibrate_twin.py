@@ -55,16 +55,16 @@ def main():
     # that survive both the true and the perturbed parameters
     probe = dpLGAR(cfg, theta_r=thr, theta_e=the, columns=x_all.shape[0], device=dev)
     with torch.no_grad():
-        ok = probe.forward_record(x_all, outputs=("runoff",))["status"] == 0
+        ok = probe.forward_record(x_all, outputs=("runoff",), on_status="ignore")["status"] == 0
         probe.alpha[0].mul_(perturb[0]); probe.n[0].mul_(perturb[1]); probe.ksat[0].mul_(perturb[2])
-        ok &= probe.forward_record(x_all, outputs=("runoff",))["status"] == 0
+        ok &= probe.forward_record(x_all, outputs=("runoff",), on_status="ignore")["status"] == 0
     keep = ok.nonzero().flatten().cpu().numpy()[:a.sites]
     assert len(keep) == a.sites, f"only {len(keep)} usable records"
     x = np.ascontiguousarray(x_all[keep])
     truth = dpLGAR(cfg, theta_r=thr, theta_e=the, columns=a.sites, device=dev)
     true_params = [[float(p) for p in pl] for pl in (truth.alpha, truth.n, truth.ksat)]
     with torch.no_grad():
-        y = truth.forward_record(x, outputs=("runoff",))["runoff"].transpose(0, 1).cpu()  # [sites, T]
+        y = truth.forward_record(x, outputs=("runoff",), on_status="ignore")["runoff"].transpose(0, 1).cpu()  # [sites, T]
     model = dpLGAR(cfg, theta_r=thr, theta_e=the, columns=a.sites, device=dev)
     with torch.no_grad():  # perturbed start (top layer matters for runoff)
         model.alpha[0].mul_(perturb[0]); model.n[0].mul_(perturb[1]); model.ksat[0].mul_(perturb[2])
