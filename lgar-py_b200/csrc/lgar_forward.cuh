@@ -536,6 +536,40 @@ __device__ void load_params(const KParams& K, int b, Tile<FM, R>& T) {
   C.pdm = __ldg(p.ponded_depth_max + b);
 }
 
+// ------------------------------------------------------------------------------------
+// Forcing tiles.  A warp's 32 columns normally share one forcing record (columns of a site are adjacent; the
+// balanced placement keeps them together): the rows of the current chunk are then staged into shared memory in blocks of
+// FORCING_BLOCK rows (1 KB) by ONE bulk asynchronous copy (TMA engine: cp.async.bulk global -> shared, completion
+// signalled on an mbarrier) issued by lane 0, and every step reads its (P, PET) pair as a shared-memory broadcast.
+// Warps whose lanes mix sites (tile straddling two sites, per-column records) read through the read-only path.
+// ------------------------------------------------------------------------------------
+constexpr int FORCING_BLOCK = 64;
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LGAR_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LGAR_DONE_%=;\n"
+      "bra LGAR_WAIT_%=;\n"
+      "LGAR_DONE_%=:\n"
+      "}\n" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 // resident CTAs per SM are bounded by the shared-memory front lists: 1 (FM = 32, the fallback for the rare columns
 // that overflow 16 fronts), 2 (FM = 16), 3 (FM = 12), 4 (FM = 8); the register cap follows from that
 template <int FM, bool COUNT, bool DUMP>
@@ -545,10 +579,14 @@ __global__ void __launch_bounds__(NT, (FM == 32) ? 1 : ((FM == 16) ? 2 : ((FM ==
   double* sm_nodes = sm_fields + 5 * FM * NT;                                    // [WARPS][NODEBUF]
   uint8_t* sm_flags = reinterpret_cast<uint8_t*>(sm_nodes + WARPS * NODEBUF);    // [FM][NT]
   __shared__ unsigned long long sm_item[WARPS];
-  pow_tables_to_shared();
-
+  __shared__ __align__(16) double2 sm_forcing[WARPS][FORCING_BLOCK];
+  __shared__ __align__(8) uint64_t sm_fbar[WARPS];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  if (lane == 0) mbar_init(&sm_fbar[warp], 1);
+  pow_tables_to_shared();  // (ends with __syncthreads: the barriers are initialised for everybody)
+  unsigned fphase = 0;     // parity of the next completion of this warp's forcing barrier
+
   double* nodebuf = sm_nodes + warp * NODEBUF;
   const lgar_problem& p = K.p;
   const int Tn = p.num_steps;
@@ -642,9 +680,25 @@ __global__ void __launch_bounds__(NT, (FM == 32) ? 1 : ((FM == 16) ? 2 : ((FM ==
     precompute_psi_wp(T, p.wilting_point_psi);
     const int site = (p.site_index && valid) ? __ldg(p.site_index + b) : 0;
     const double* frc = p.forcing + (size_t)site * Tn * 2;
+    // one forcing record for the whole warp?  (lanes beyond B follow lane 0)
+    const int site0 = __shfl_sync(0xffffffffu, site, 0);
+    const bool staged = __all_sync(0xffffffffu, !valid || site == site0);
+    const double2* frc0 = reinterpret_cast<const double2*>(p.forcing + (size_t)site0 * Tn * 2);
 
     for (int t = t0; t < t1; t++) {
-      const double2 x = __ldg(reinterpret_cast<const double2*>(frc) + t);
+      const int fk = (t - t0) & (FORCING_BLOCK - 1);
+      if (staged && fk == 0) {
+        const int rows = min(t1 - t, FORCING_BLOCK);
+        __syncwarp();  // every lane has read the previous block
+        if (lane == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // order those reads before the async write
+          mbar_expect_tx(&sm_fbar[warp], (uint32_t)rows * 16u);
+          bulk_copy_g2s(&sm_forcing[warp][0], frc0 + t, (uint32_t)rows * 16u, &sm_fbar[warp]);
+        }
+        mbar_wait(&sm_fbar[warp], fphase);
+        fphase ^= 1u;
+      }
+      const double2 x = staged ? sm_forcing[warp][fk] : __ldg(reinterpret_cast<const double2*>(frc) + t);
 #pragma unroll
       for (int k = 0; k < NOUT; k++) T.acc[k] = 0.0;
       const bool alive = valid && (T.ctx.st == 0);
