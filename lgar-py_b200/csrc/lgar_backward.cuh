@@ -4,7 +4,12 @@
 // dL/d(alpha, n, ksat)[L][B] for L = sum_{k,t,b} g[k][t][b] * out[k][t][b] (+ the same with the
 // per-column sums), with the reference's autograd semantics.
 //
-// One WARP owns a tile of 32 columns and walks its forcing record backwards, chunk by chunk:
+// Work item = (tile of 32 columns, chunk of the forcing record), handed out from one counter LAST CHUNK FIRST to the
+// resident warps; item (tile, c) needs the adjoint state that item (tile, c+1) left behind (lambda of the column
+// state, the running parameter gradients), which was handed out `ntiles` items earlier and is therefore finished or
+// running on a resident warp: an acquire-spin on rev_done[tile] orders them without any possibility of deadlock.
+// (Tiles cost between 0.5x and 1.7x the mean; with whole records per warp the launch lasted as long as the
+// unluckiest warp's three or four tiles.)  For its item a warp:
 //   1. load the chunk-start checkpoint the forward kernel stored (lgar_forward(keep_checkpoints));
 //   2. recompute the chunk forward with R = Var: every sub-step records its own tape (leaves = the
 //      state in front of it; it takes exactly the forward kernel's branches because the values come
@@ -61,8 +66,11 @@ struct BParams {
   TapeEntry* tape;              // [slots][arena_cap][32]: the tapes of all sub-steps of one chunk, back to back
   unsigned char* meta;          // [slots][ring_steps][32] StepMeta
   double* adj;                  // [slots][num_leaves + step_cap][32]
-  double* lam;                  // [slots][num_leaves][32]
-  unsigned long long* next_tile;
+  double* lam;                  // [ntiles][num_leaves][32]: adjoint of the column state between chunks
+  double* gpar;                 // [ntiles][NPAR_IDS][32]: running parameter gradients between chunks
+  int32_t* rev_done;            // [ntiles] chunks of the reverse pass completed per tile
+  int32_t* rev_flags;           // [ntiles][32] tape overflow seen so far
+  unsigned long long* next_tile;  // item counter
   int32_t ring_steps;           // chunk_steps * S
   int32_t arena_cap;            // tape entries per lane for one chunk
   int32_t step_cap;             // max entries of one sub-step (ids are 16 bit)
@@ -93,12 +101,13 @@ __global__ void lgar_reduce_tile_partials(const double* partials, int ntiles, in
 __host__ inline size_t backward_meta_bytes(int FM) {
   return FM == 16 ? sizeof(StepMeta<16>) : (FM == 12 ? sizeof(StepMeta<12>) : sizeof(StepMeta<8>));
 }
-__host__ inline size_t backward_scratch_bytes(int S, int FM, int chunk, int slots, int arena_cap, int step_cap) {
+__host__ inline size_t backward_scratch_bytes(int S, int FM, int chunk, int slots, int arena_cap, int step_cap, int ntiles) {
   const size_t ring_steps = (size_t)chunk * S;
   const size_t nl = NPAR_IDS + 5 * (size_t)FM + 2 + NGIUH;
   size_t per = (size_t)arena_cap * 32 * sizeof(TapeEntry) + ring_steps * 32 * backward_meta_bytes(FM) +
-               (nl + step_cap) * 32 * 8 + nl * 32 * 8;
-  return per * slots + 8192;
+               (nl + step_cap) * 32 * 8;
+  size_t per_tile = nl * 32 * 8 + (size_t)NPAR_IDS * 32 * 8 + 32 * 4 + 4;
+  return per * slots + per_tile * ntiles + 16384;
 }
 
 // GM = 0: trapezoid Geff only (closed-form branch compiled out of the taped sub-step); GM = 2: run-time switch
@@ -125,7 +134,6 @@ __global__ void __launch_bounds__(NT, 2) lgar_backward_kernel(const BParams P) {
   TapeEntry* arena = P.tape + (size_t)slot * P.arena_cap * 32 + lane;
   StepMeta<FM>* metas = reinterpret_cast<StepMeta<FM>*>(P.meta) + (size_t)slot * P.ring_steps * 32 + lane;  // [j * 32]
   double* adj = P.adj + (size_t)slot * (NL + P.step_cap) * 32 + lane;
-  double* lam = P.lam + (size_t)slot * NL * 32 + lane;
   TapeCtl& tc = g_tapectl[threadIdx.x];
   tc.first_id = NL;
 
@@ -135,18 +143,32 @@ __global__ void __launch_bounds__(NT, 2) lgar_backward_kernel(const BParams P) {
   Tv.col.gb = sm_flags + threadIdx.x;
   Tv.ctx.iter_cap = K.iter_cap;
   Column<FM, Var>& C = Tv.col;
+  const unsigned long long nitems = (unsigned long long)K.ntiles * K.nchunks;
 
   for (;;) {
     if (lane == 0) sm_item[warp] = atomicAdd(P.next_tile, 1ULL);
     __syncwarp();
-    const unsigned long long tile = sm_item[warp];
+    const unsigned long long item = sm_item[warp];
     __syncwarp();
-    if (tile >= (unsigned long long)K.ntiles) break;
-    const int slot_c = (int)tile * 32 + lane;   // position in the tile grid (checkpoints); b = ensemble column
+    if (item >= nitems) break;
+    const int chunk = K.nchunks - 1 - (int)(item / K.ntiles);   // last chunk first
+    const int tile = (int)(item % K.ntiles);
+    const bool first_item = (chunk == K.nchunks - 1);
+    if (!first_item) {  // wait for the adjoint state of chunk + 1 (acquire)
+      if (lane == 0) {
+        volatile int32_t* d = P.rev_done + tile;
+        while (*d < K.nchunks - 1 - chunk) __nanosleep(200);
+      }
+      __syncwarp();
+      __threadfence();
+    }
+    const int slot_c = tile * 32 + lane;   // position in the tile grid (checkpoints); b = ensemble column
     const bool valid = (size_t)slot_c < B;
     const int slot_cc = valid ? slot_c : (int)B - 1;
     const int b = p.column_order ? __ldg(p.column_order + slot_cc) : slot_cc;
     const int bb = b;
+    double* lam = P.lam + (size_t)tile * NL * 32 + lane;
+    double* gsave = P.gpar + (size_t)tile * NPAR_IDS * 32 + lane;
 
     // final status of the forward pass: steps at and after the crash step have no gradient
     const int final_st = __ldcg(K.state_i + ((size_t)K.nchunks * NI_STATE + 2) * K.Bp + slot_cc);
@@ -162,14 +184,20 @@ __global__ void __launch_bounds__(NT, 2) lgar_backward_kernel(const BParams P) {
     }
     const int site = (p.site_index && valid) ? __ldg(p.site_index + b) : 0;
     const double* frc = p.forcing + (size_t)site * Tn * 2;
-    for (int q = 0; q < NL; q++) lam[(size_t)q * 32] = 0.0;
     double gpar[NPAR_IDS];
-#pragma unroll
-    for (int q = 0; q < NPAR_IDS; q++) gpar[q] = 0.0;
     bool overflow = false;
+    if (first_item) {
+      for (int q = 0; q < NL; q++) __stcg(lam + (size_t)q * 32, 0.0);
+#pragma unroll
+      for (int q = 0; q < NPAR_IDS; q++) gpar[q] = 0.0;
+    } else {
+#pragma unroll
+      for (int q = 0; q < NPAR_IDS; q++) gpar[q] = __ldcg(gsave + (size_t)q * 32);
+      overflow = __ldcg(P.rev_flags + (size_t)tile * 32 + lane) != 0;
+    }
     unsigned long long cyc_fwd = 0, cyc_rev = 0, n_entries = 0, n_sub = 0;
 
-    for (int chunk = K.nchunks - 1; chunk >= 0; chunk--) {
+    {
       const long long clk_a = clock64();
       const int t0 = chunk * K.chunk_steps;
       const int t1 = min(Tn, t0 + K.chunk_steps);
@@ -240,12 +268,12 @@ __global__ void __launch_bounds__(NT, 2) lgar_backward_kernel(const BParams P) {
 #pragma unroll
             for (int k = 0; k < 5; k++) {
               const int id = M.id_field[k * FM + i];
-              if (id >= 0) adj[(size_t)id * 32] += lam[(size_t)(leaf_fields<FM>() + k * FM + i) * 32];
+              if (id >= 0) adj[(size_t)id * 32] += __ldcg(lam + (size_t)(leaf_fields<FM>() + k * FM + i) * 32);
             }
-          if (M.id_ponded >= 0) adj[(size_t)M.id_ponded * 32] += lam[(size_t)leaf_ponded<FM>() * 32];
-          if (M.id_endvol >= 0) adj[(size_t)M.id_endvol * 32] += lam[(size_t)leaf_endvol<FM>() * 32];
+          if (M.id_ponded >= 0) adj[(size_t)M.id_ponded * 32] += __ldcg(lam + (size_t)leaf_ponded<FM>() * 32);
+          if (M.id_endvol >= 0) adj[(size_t)M.id_endvol * 32] += __ldcg(lam + (size_t)leaf_endvol<FM>() * 32);
           for (int i = 0; i < NGIUH; i++)
-            if (M.id_giuh[i] >= 0) adj[(size_t)M.id_giuh[i] * 32] += lam[(size_t)(leaf_giuh<FM>() + i) * 32];
+            if (M.id_giuh[i] >= 0) adj[(size_t)M.id_giuh[i] * 32] += __ldcg(lam + (size_t)(leaf_giuh<FM>() + i) * 32);
           // dL / d(outputs of this forcing step)
 #pragma unroll
           for (int k = 0; k < NOUT; k++) {
@@ -269,7 +297,7 @@ __global__ void __launch_bounds__(NT, 2) lgar_backward_kernel(const BParams P) {
               if (te.b >= 0) adj[(size_t)te.b * 32] += g * te.db;
             }
           }
-          for (int q = NPAR_IDS; q < NL; q++) lam[(size_t)q * 32] = adj[(size_t)q * 32];
+          for (int q = NPAR_IDS; q < NL; q++) __stcg(lam + (size_t)q * 32, adj[(size_t)q * 32]);
 #pragma unroll
           for (int q = 0; q < NPAR_IDS; q++) gpar[q] += adj[(size_t)q * 32];
         }
@@ -277,9 +305,15 @@ __global__ void __launch_bounds__(NT, 2) lgar_backward_kernel(const BParams P) {
       __syncwarp();
       cyc_rev += (unsigned long long)(clock64() - clk_b);
     }
+    if (chunk > 0) {
+      // hand the running state to the item (tile, chunk - 1): lambda is already in place (global memory)
+#pragma unroll
+      for (int q = 0; q < NPAR_IDS; q++) gsave[(size_t)q * 32] = gpar[q];
+      P.rev_flags[(size_t)tile * 32 + lane] = overflow ? 1 : 0;
+    }
     // ---- the initial state depends on the parameters: theta_init = theta_l(psi_init), K_init
     //      (data/utils.py:82-84, WettingFront.py:38-48); ending_volume(0) = mass_balance()
-    {
+    if (chunk == 0) {
       tc.base = arena;
       tc.n = 0;
       tc.cap = min(P.step_cap, P.arena_cap);
@@ -297,9 +331,9 @@ __global__ void __launch_bounds__(NT, 2) lgar_backward_kernel(const BParams P) {
 #pragma unroll
           for (int k = 0; k < 5; k++) {
             const int id = C.fid(k, i);
-            if (id >= 0) adj[(size_t)id * 32] += lam[(size_t)(leaf_fields<FM>() + k * FM + i) * 32];
+            if (id >= 0) adj[(size_t)id * 32] += __ldcg(lam + (size_t)(leaf_fields<FM>() + k * FM + i) * 32);
           }
-        if (C.ending_volume.id >= 0) adj[(size_t)C.ending_volume.id * 32] += lam[(size_t)leaf_endvol<FM>() * 32];
+        if (C.ending_volume.id >= 0) adj[(size_t)C.ending_volume.id * 32] += __ldcg(lam + (size_t)leaf_endvol<FM>() * 32);
         for (int e = ne - 1; e >= 0; e--) {
           const double g = adj[(size_t)(NL + e) * 32];
           if (g != 0.0) {
@@ -312,7 +346,9 @@ __global__ void __launch_bounds__(NT, 2) lgar_backward_kernel(const BParams P) {
         for (int q = 0; q < NPAR_IDS; q++) gpar[q] += adj[(size_t)q * 32];
       }
     }
-    if (P.reduce) {
+    if (chunk > 0) {
+      // (nothing to write yet)
+    } else if (P.reduce) {
       // shared parameters: sum over the 32 columns of the tile in a fixed (butterfly) order; overflowed and
       // out-of-range lanes contribute 0
 #pragma unroll
@@ -330,7 +366,7 @@ __global__ void __launch_bounds__(NT, 2) lgar_backward_kernel(const BParams P) {
         P.grad_ksat[(size_t)l * B + b] = overflow ? qnan : gpar[3 * l + 2];
       }
     }
-    if (valid && P.tape_overflow) P.tape_overflow[b] = overflow ? 1 : 0;
+    if (chunk == 0 && valid && P.tape_overflow) P.tape_overflow[b] = overflow ? 1 : 0;
     if (P.counters) {
       if (lane == 0) {
         atomicAdd(P.counters + 0, cyc_fwd);
@@ -339,10 +375,13 @@ __global__ void __launch_bounds__(NT, 2) lgar_backward_kernel(const BParams P) {
       if (valid) {
         atomicAdd(P.counters + 2, n_entries);
         atomicAdd(P.counters + 3, n_sub);
-        if (overflow) atomicAdd(P.counters + 4, 1ULL);
+        if (chunk == 0 && overflow) atomicAdd(P.counters + 4, 1ULL);
       }
     }
+    // publish (release): the adjoint state of this chunk is complete
+    __threadfence();
     __syncwarp();
+    if (lane == 0) atomicExch(P.rev_done + tile, K.nchunks - chunk);
   }
 }
 

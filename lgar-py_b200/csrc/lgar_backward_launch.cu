@@ -37,6 +37,7 @@ static int launch_backward(BParams& P, int S, int chunk, int slots, int arena_ca
   long long grid = (long long)num_sms * per_sm;
   if (grid > slots / WARPS) grid = slots / WARPS;
   if (grid < 1) grid = 1;
+  const int ntiles = P.K.ntiles;
   const size_t ring_steps = (size_t)chunk * S;
   const size_t nl = num_leaves<FM>();
   size_t o = 0;
@@ -44,12 +45,16 @@ static int launch_backward(BParams& P, int S, int chunk, int slots, int arena_ca
   P.tape = (TapeEntry*)take((size_t)slots * arena_cap * 32 * sizeof(TapeEntry));
   P.meta = (unsigned char*)take((size_t)slots * ring_steps * 32 * sizeof(StepMeta<FM>));
   P.adj = (double*)take((size_t)slots * (nl + step_cap) * 32 * 8);
-  P.lam = (double*)take((size_t)slots * nl * 32 * 8);
+  P.lam = (double*)take((size_t)ntiles * nl * 32 * 8);
+  P.gpar = (double*)take((size_t)ntiles * NPAR_IDS * 32 * 8);
+  P.rev_flags = (int32_t*)take((size_t)ntiles * 32 * 4);
+  P.rev_done = (int32_t*)take((size_t)ntiles * 4);
   P.next_tile = (unsigned long long*)take(64);
   P.ring_steps = (int32_t)ring_steps;
   P.arena_cap = arena_cap;
   P.step_cap = step_cap;
   BW_TRY(cudaMemsetAsync(P.next_tile, 0, 64, st));
+  BW_TRY(cudaMemsetAsync(P.rev_done, 0, (size_t)ntiles * 4, st));
   kern<<<(unsigned)grid, NT, smem, st>>>(P);
   BW_TRY(cudaGetLastError());
   if (P.reduce) {

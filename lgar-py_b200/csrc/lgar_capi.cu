@@ -115,7 +115,7 @@ int backward_arena_cap(const Shape& s) {
   return (int)c;
 }
 int backward_slots(const Shape& s) {
-  long long want = ((long long)s.ntiles + lgar::WARPS - 1) / lgar::WARPS;
+  long long want = ((long long)s.ntiles * s.nchunks + lgar::WARPS - 1) / lgar::WARPS;
   long long grid = 160LL * backward_ctas_per_sm(s);
   if (grid > want) grid = want;
   return (int)grid * lgar::WARPS;
@@ -245,7 +245,7 @@ size_t lgar_workspace_bytes(const lgar_problem* p, int with_grad) {
   size_t total = carve(s, with_grad).total;
 #ifdef LGAR_WITH_BACKWARD
   if (with_grad)
-    total += lgar::backward_scratch_bytes(s.S, s.FM, s.chunk, backward_slots(s), backward_arena_cap(s), LGAR_TAPE_CAP);
+    total += lgar::backward_scratch_bytes(s.S, s.FM, s.chunk, backward_slots(s), backward_arena_cap(s), LGAR_TAPE_CAP, s.ntiles);
 #endif
   return total;
 }
