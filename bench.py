@@ -66,6 +66,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="A/B: stream-ordered windows (no programmatic dependent launch)")
     ap.add_argument("--e2e-interleaved", action="store_true", help="A/B: D2H of every segment right behind its launch")
+    ap.add_argument("--no-balance", action="store_true", help="A/B: identity placement of columns on warps")
     ap.add_argument("--no-pyref", action="store_true", help="reference arm: skip the Python reference (port only)")
     ap.add_argument("--pyref-rows", type=int, default=0, help="reference arm: forcing rows per step of the Python reference")
     ap.add_argument("--pyref-procs", type=int, default=0, help="reference arm: processes of the Python reference (default min(8, cores))")
@@ -357,6 +358,8 @@ def main():
     ens = ColumnEnsemble(theta_r=we.theta_r, theta_e=we.theta_e, thickness=we.thickness, forcing=we.forcing,
                          site_index=we.site_index, max_fronts=args.max_fronts, chunk_steps=args.chunk, device=dev)
     d_alpha, d_n, d_ksat = (host[k].to(dev) for k in ("alpha", "n", "ksat"))
+    if not args.no_balance:
+        ens.balance(d_ksat)   # placement of columns on warps by (site, top-layer ksat): lgar_problem.column_order
     outs = ("runoff", "AET")  # per-step series kept in HBM: 2 x T x B x 8 B
 
     def barrier():
@@ -524,6 +527,8 @@ def main():
                                    forcing=we.forcing, site_index=we.site_index[:Bg], max_fronts=args.max_fronts,
                                    chunk_steps=args.chunk, device=dev)
             Ag, Ng, Kg = (x[:, :Bg].contiguous() for x in (d_alpha, d_n, d_ksat))
+            if not args.no_balance:
+                ens_g.balance(Kg)
         alive_g = int(alive_cols[:Bg].sum())
         barrier()
         g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True); gm = torch.cuda.Event(enable_timing=True)
@@ -599,6 +604,7 @@ def main():
                                   "FRONT_OVERFLOW (>16 fronts) and ITER_CAP (a root finder above 1e6 iterations, where the "
                                   "reference keeps looping for hours) are capacity limits of this library, not reference states",
                    "alive_column_steps_per_gpu": alive_steps, "max_fronts": args.max_fronts, "chunk_steps": args.chunk,
+                   "placement": "identity" if args.no_balance else "columns sorted by (site, top-layer ksat) (ColumnEnsemble.balance)",
                    "l2": "working set per step (per-step outputs %d x %d x B x 8 B = %.2f GB) exceeds the 126 MB L2; no flush needed"
                          % (len(outs), segs[0][1] - segs[0][0], len(outs) * (segs[0][1] - segs[0][0]) * B * 8 / 1e9)},
         "gpu_launches": nseg,

@@ -215,7 +215,8 @@ int lgar_backward(const lgar_problem* p, const double* grad_per_step, uint32_t g
  *                   (per-column mode: NaN) and the caller must not step on it.
  *   partials        [ceil(B/32)][3 L] doubles of scratch for reduce != 0.
  *   counters        [8] or NULL, diagnostics summed over warps: 0 cycles in the taped recompute, 1 cycles in the
- *                   reverse sweeps, 2 tape entries recorded (per lane), 3 sub-steps taped (per lane), 4 overflowed columns. */
+ *                   reverse sweeps, 2 tape entries recorded (per lane), 3 sub-steps taped (per lane), 4 overflowed columns,
+ *                   5-7 cycles of the taped recompute in the move sweep, in calc_dzdt (Geff), in the other Geff phases. */
 typedef struct lgar_gradients {
   const double* grad_per_step;  /* [popcount(grad_mask)][T][B] dL/d(per-step outputs) or NULL                */
   uint32_t grad_mask;

@@ -196,6 +196,8 @@ __global__ void __launch_bounds__(NT, 2) lgar_backward_kernel(const BParams P) {
       overflow = __ldcg(P.rev_flags + (size_t)tile * 32 + lane) != 0;
     }
     unsigned long long cyc_fwd = 0, cyc_rev = 0, n_entries = 0, n_sub = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) Tv.ctx.ph[k] = 0;
 
     {
       const long long clk_a = clock64();
@@ -371,6 +373,8 @@ __global__ void __launch_bounds__(NT, 2) lgar_backward_kernel(const BParams P) {
       if (lane == 0) {
         atomicAdd(P.counters + 0, cyc_fwd);
         atomicAdd(P.counters + 1, cyc_rev);
+#pragma unroll
+        for (int k = 0; k < 3; k++) atomicAdd(P.counters + 5 + k, Tv.ctx.ph[k == 0 ? 1 : (k == 1 ? 3 : 0)] + (k == 2 ? Tv.ctx.ph[2] : 0ULL));
       }
       if (valid) {
         atomicAdd(P.counters + 2, n_entries);

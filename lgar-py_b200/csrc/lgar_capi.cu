@@ -370,6 +370,7 @@ int lgar_backward_ex(const lgar_problem* p, const lgar_gradients* g, void* works
   P.reduce = g->reduce ? 1 : 0;
   P.partials = g->partials;
   P.counters = g->counters;
+  K.time_phases = g->counters ? 1 : 0;
   if (g->counters) CUDA_TRY(cudaMemsetAsync(g->counters, 0, 8 * sizeof(unsigned long long), st));
   unsigned char* scratch = w + c.total;
   return lgar_reverse_unit_launch(s.FM, &P, s.S, s.chunk, backward_slots(s), backward_arena_cap(s), LGAR_TAPE_CAP, g_num_sms,

@@ -47,6 +47,7 @@ struct KParams {
   // leaves.  `overlap`: the previous window may still be running, so even the first chunk of a tile waits for the
   // tile's progress counter.
   int32_t seq, slot, overlap;
+  int32_t time_phases;   // reverse kernel diagnostics: accumulate the phase timers of substep() in Ctx::ph
   int32_t keep_ckpt;     // 1: state of chunk c is stored at index c (+ final at nchunks)
   long long iter_cap;
 };
@@ -151,7 +152,7 @@ __device__ void substep(Tile<FM, R>& T, bool act, double precip_rate, double pet
   const bool brA = act && create && !saturated;             // create a surficial front
   const bool brB = act && !create && (ponded_depth_sub > 0.0);  // insert water
 
-  const bool timed = (GM == 2) && K.o.counters != nullptr;  // counting instantiations only
+  const bool timed = ((GM == 2) && K.o.counters != nullptr) || K.time_phases;  // counting instantiations / reverse diagnostics
   long long tph = timed ? clock64() : 0;
   // ---- phase 1: Layer.insert_water (Layer.py:1418-1536) for branch-B lanes
   {

@@ -29,6 +29,6 @@ for B, T in shapes:
     gn = A.grad[:, ok]
     rc = ens.last_reverse_counters.cpu().numpy().astype(np.float64)
     print(f"  reverse kernel: taped recompute {100 * rc[0] / max(rc[0] + rc[1], 1):.1f} % of warp cycles, reverse sweeps "
-          f"{100 * rc[1] / max(rc[0] + rc[1], 1):.1f} %; {rc[2] / max(rc[3], 1):.1f} tape entries per sub-step; overflowed columns {int(rc[4])}", flush=True)
+          f"{100 * rc[1] / max(rc[0] + rc[1], 1):.1f} %; {rc[2] / max(rc[3], 1):.1f} tape entries per sub-step; overflowed columns {int(rc[4])}; of the recompute: move sweep {100 * rc[5] / max(rc[0], 1):.1f} %, calc_dzdt Geff {100 * rc[6] / max(rc[0], 1):.1f} %, other Geff {100 * rc[7] / max(rc[0], 1):.1f} %", flush=True)
     print(f"B={B} T={T}: fwd {f:.0f} ms, bwd {b:.0f} ms -> fwd+grad {alive/(f+b)*1e3:.4g} col-steps/s (fwd alone {alive/f*1e3:.4g}); "
           f"grad finite frac {float(torch.isfinite(gn).float().mean()):.4f}  |dL/dalpha0| mean {float(gn[0].abs().nanmean()):.3g}", flush=True)
