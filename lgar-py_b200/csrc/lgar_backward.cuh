@@ -136,6 +136,9 @@ __global__ void __launch_bounds__(NT, 2) lgar_backward_kernel(const BParams P) {
   double* adj = P.adj + (size_t)slot * (NL + P.step_cap) * 32 + lane;
   TapeCtl& tc = g_tapectl[threadIdx.x];
   tc.first_id = NL;
+  // Geff partials of the taped recompute go through the warp's adjoint array (idle until the reverse sweep)
+  if (lane == 0) g_geffq_partials[warp] = P.adj + (size_t)slot * (NL + P.step_cap) * 32;
+  __syncwarp();
 
   Tile<FM, Var> Tv;
   Tv.col.fb = sm_fields + threadIdx.x;
@@ -291,12 +294,25 @@ __global__ void __launch_bounds__(NT, 2) lgar_backward_kernel(const BParams P) {
             else id = M.id_acc[k];
             if (id >= 0) adj[(size_t)id * 32] += g;
           }
-          for (int e = ne - 1; e >= 0; e--) {
-            const double g = adj[(size_t)(NL + e) * 32];
-            if (g != 0.0) {
-              const TapeEntry te = tape[(size_t)e * 32];
-              if (te.a >= 0) adj[(size_t)te.a * 32] += g * te.da;
-              if (te.b >= 0) adj[(size_t)te.b * 32] += g * te.db;
+          // the tape comes back from DRAM (the arenas of all resident warps are far larger than L2): fetch eight
+          // entries at a time, independently of the adjoints, so that the misses overlap instead of queueing behind
+          // the dependent chain adj -> entry -> adj
+          for (int e0 = ne - 1; e0 >= 0; e0 -= 8) {
+            TapeEntry te8[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+              if (e0 - k >= 0) te8[k] = tape[(size_t)(e0 - k) * 32];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+              const int e = e0 - k;
+              if (e >= 0) {
+                const double g = adj[(size_t)(NL + e) * 32];
+                if (g != 0.0) {
+                  const TapeEntry te = te8[k];
+                  if (te.a >= 0) adj[(size_t)te.a * 32] += g * te.da;
+                  if (te.b >= 0) adj[(size_t)te.b * 32] += g * te.db;
+                }
+              }
             }
           }
           for (int q = NPAR_IDS; q < NL; q++) __stcg(lam + (size_t)q * 32, adj[(size_t)q * 32]);

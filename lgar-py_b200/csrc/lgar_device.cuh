@@ -33,7 +33,7 @@ namespace lgar {
 constexpr int NT = 128;          // threads per CTA (4 warps, each warp an independent tile)
 constexpr int WARPS = NT / 32;
 constexpr int NODEBUF = 136;     // doubles of per-warp scratch: Geff request queue (forward), node buffer of the A/B path
-constexpr int NODEBUF_TAPED = 256;  // taped pass: the queue also returns five partials per request
+constexpr int NODEBUF_TAPED = NODEBUF;  // (the taped pass returns its five partials per request through global scratch)
 constexpr int MAXL = LGAR_MAX_LAYERS;
 constexpr int NGIUH = LGAR_MAX_GIUH;
 constexpr int NOUT = LGAR_NUM_OUTPUTS;
@@ -883,10 +883,12 @@ struct GeffQueue {         // SoA over the 32 slots of a batch; lives in the per
   double b[32];            // in: theta_2
   int meta[32];            // in: owner lane | list layer << 8; -1 = empty slot
   int st[32];              // out: lgar_status raised inside calc_geff (0 = none)
-  double d[5][32];         // out (taped pass only): d Geff / d(theta_1, theta_2, alpha, n, m)
 };
-constexpr int GEFFQ_DOUBLES_FWD = (32 * 8 * 2 + 32 * 4 * 2) / 8;   // forward kernel: without the partials
-constexpr int GEFFQ_DOUBLES_BWD = (int)(sizeof(GeffQueue) / 8);
+static_assert(sizeof(GeffQueue) <= NODEBUF * sizeof(double), "the queue lives in the per-warp scratch");
+// taped pass only: d Geff / d(theta_1, theta_2, alpha, n, m) of the 32 slots, [5][32] doubles per warp.  Kept in GLOBAL
+// scratch (the warp's adjoint array, idle during the taped recompute): 1.25 KB more shared memory per warp would cost
+// the reverse kernel its second CTA per SM.
+__shared__ double* g_geffq_partials[NT / 32];
 
 struct K4 {
   double k[4];
@@ -1171,11 +1173,12 @@ __device__ __noinline__ void geff_batch_eval_taped(GeffQueue* q, const ST* soil,
     const double inv_span = 1.0 / (s.the - s.thr);
     q->a[lane] = value;
     q->st[lane] = st;
-    q->d[0][lane] = f * (dG_dhi * pi.a + dh * Csei) * inv_span;
-    q->d[1][lane] = f * (dG_dhf * pf.a) * inv_span;
-    q->d[2][lane] = f * (dh * Ca + dG_dhi * pi.b + dG_dhf * pf.b);
-    q->d[3][lane] = f * (dh * Cn + dG_dhi * pi.c + dG_dhf * pf.c);
-    q->d[4][lane] = f * (dh * Cm + dG_dhi * pi.d + dG_dhf * pf.d);
+    double* dq = g_geffq_partials[threadIdx.x >> 5] + lane;
+    dq[0 * 32] = f * (dG_dhi * pi.a + dh * Csei) * inv_span;
+    dq[1 * 32] = f * (dG_dhf * pf.a) * inv_span;
+    dq[2 * 32] = f * (dh * Ca + dG_dhi * pi.b + dG_dhf * pf.b);
+    dq[3 * 32] = f * (dh * Cn + dG_dhi * pi.c + dG_dhf * pf.c);
+    dq[4 * 32] = f * (dh * Cm + dG_dhi * pi.d + dG_dhf * pf.d);
   }
   __syncwarp();
 }
@@ -1206,7 +1209,8 @@ __device__ __forceinline__ Var geffq_get(GeffQueue* q, int slot, const Var& t1, 
   const int st = q->st[slot];
   if (st) raise(c, st);
   const int ids[5] = {t1.id, t2.id, s.id_alpha, s.id_n, s.id_m};
-  const double d[5] = {q->d[0][slot], q->d[1][slot], q->d[2][slot], q->d[3][slot], q->d[4][slot]};
+  const double* dq = g_geffq_partials[threadIdx.x >> 5] + slot;
+  const double d[5] = {dq[0 * 32], dq[1 * 32], dq[2 * 32], dq[3 * 32], dq[4 * 32]};
   return tape_record_n(q->a[slot], 5, ids, d);
 }
 __device__ __forceinline__ void geffq_eval(GeffQueue* q, const SoilT<double>* soil, int L, int nint) {
