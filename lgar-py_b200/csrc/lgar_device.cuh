@@ -1183,6 +1183,225 @@ __device__ __noinline__ void geff_batch_eval_taped(GeffQueue* q, const ST* soil,
   __syncwarp();
 }
 
+// ------------------------------------------------------------------------------------
+// Split batches: EIGHT lanes per request, at most four requests per batch.  A full batch costs the latency of one
+// whole request (~480 dependent pows) however many of its 32 slots are filled, so the remainder of a phase's
+// requests (R mod 32, when it is small) goes through split batches instead: sub-lane p of a group evaluates the
+// nodes p*npl+1 .. (p+1)*npl (npl = ceil(nint / 8) = 15), whose abscissae h_i + dh + ... + dh (the rounded chain of
+// the reference) come from advance_rounded(); the trapezoid terms stay in registers, and the closing sum -- which
+// must be added up in the reference's order to give the same bits -- is handed from sub-lane to sub-lane.
+// Latency: 60 pows + 120 dependent adds instead of 480 pows.  Values are bit-identical to the full batch.
+// ------------------------------------------------------------------------------------
+constexpr int GEFF_SPLIT_SLOTS = 4;
+constexpr int GEFF_SPLIT_MAX_NODES = 16;  // per sub-lane (nint <= 128)
+
+__device__ __forceinline__ double geff_split_start(double h_i, double dh, int first) {
+  double h = advance_rounded(h_i, dh, first);
+  if (!(h > 0.0)) {  // outside the positive range of the exact jump: walk the chain
+    h = h_i;
+    for (int w = 0; w < first; w++) h = h + dh;
+  }
+  return h;
+}
+
+template <class ST>
+__device__ __noinline__ void geff_batch_eval_split(GeffQueue* q, const ST* soil, int L, int nint) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, grp = lane >> 3, sub = lane & 7, base = lane & ~7;
+  const int meta = q->meta[grp];
+  const bool have = meta >= 0;
+  const Soil s = gather_soil(soil, L, have ? (meta & 31) : lane, have ? ((meta >> 8) & 7) : 0);
+  double h_i = 0.0, dh = 0.0, k0 = 0.0;
+  int st = 0;
+  if (have) {  // stage A, redundantly in the eight lanes of the group (same operands, same bits)
+    Ctx c;
+    c.st = 0;
+    const double se_i = se_from_theta(q->a[grp], s, c);
+    const double se_f = se_from_theta(q->b[grp], s, c);
+    const double2 hh = h_from_se_x2(se_i, se_f, s, c);
+    h_i = hh.x;
+    const double h_f = hh.y;
+    if (fabs(h_i) >= 0.1 && s.alpha * h_i < 0.0) raise(c, LGAR_ST_NEG_POW);
+    if (fabs(h_f) >= 0.1 && s.alpha * h_f < 0.0) raise(c, LGAR_ST_NEG_POW);
+    dh = (h_f - h_i) / (double)nint;
+    k0 = k_from_se(se_i, s.ksat, s.m, s.inv_m, c);
+    st = c.st;
+  }
+  const int npl = (nint + 7) >> 3;
+  const int first = sub * npl + 1;
+  const int cnt = have ? max(0, min(npl, nint - first + 1)) : 0;
+  double kk[GEFF_SPLIT_MAX_NODES];
+  double klast = 0.0;
+  int bad_first = 0;
+  if (cnt > 0) {
+    double h = geff_split_start(h_i, dh, first);
+#pragma unroll
+    for (int i = 0; i < GEFF_SPLIT_MAX_NODES; i += 2) {
+      kk[i] = kk[i + 1] = 0.0;
+      if (i < cnt) {
+        const double ha = h, hb = ha + dh;
+        h = hb + dh;
+        int bad;
+        const double2 k2 = k_nodes_core_x2(ha, hb, s.alpha, s.n, s.m, s.inv_m, s.ksat, &bad);
+        kk[i] = k2.x;
+        kk[i + 1] = k2.y;
+        klast = (i + 1 < cnt) ? k2.y : k2.x;
+        if (bad_first == 0) {
+          if (bad) bad_first = bad;
+          else if (isnan(k2.x) || (i + 1 < cnt && isnan(k2.y))) bad_first = LGAR_ST_NAN;
+        }
+      }
+    }
+  }
+  // K of the node in front of this sub-lane's first node
+  double kin = __shfl_up_sync(FULL, klast, 1);
+  if (sub == 0) kin = k0;
+  const double half = dh / 2.0;
+  double acc = 0.0;
+#pragma unroll 1
+  for (int p = 0; p < 8; p++) {
+    if (sub == p && cnt > 0) {
+      double k1 = kin;
+#pragma unroll
+      for (int i = 0; i < GEFF_SPLIT_MAX_NODES; i++) {
+        if (i < cnt) {
+          acc = acc + ((k1 + kk[i]) * half);
+          k1 = kk[i];
+        }
+      }
+    }
+    acc = __shfl_sync(FULL, acc, base + p);  // the running sum goes to the next sub-lane (and, at the end, to all)
+    const int v = __shfl_sync(FULL, bad_first, base + p);
+    if (st == 0 && v) st = v;  // guards in node order: the first node that raises wins
+  }
+  if (have && sub == 0) {
+    q->a[grp] = fabs(acc / s.ksat);
+    q->st[grp] = st;
+  }
+  __syncwarp();
+}
+
+// taped variant: value as above + the partials (plain sums over the nodes: each sub-lane adds up its share, then a
+// butterfly over the group)
+template <class ST>
+__device__ __noinline__ void geff_batch_eval_split_taped(GeffQueue* q, const ST* soil, int L, int nint) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, grp = lane >> 3, sub = lane & 7, base = lane & ~7;
+  const int meta = q->meta[grp];
+  const bool have = meta >= 0;
+  const Soil s = gather_soil(soil, L, have ? (meta & 31) : lane, have ? ((meta >> 8) & 7) : 0);
+  double h_i = 0.0, dh = 0.0, k0 = 0.0, se_i = 1.0, se_f = 1.0, h_f = 0.0;
+  int st = 0;
+  if (have) {
+    Ctx c;
+    c.st = 0;
+    se_i = se_from_theta(q->a[grp], s, c);
+    se_f = se_from_theta(q->b[grp], s, c);
+    const double2 hh = h_from_se_x2(se_i, se_f, s, c);
+    h_i = hh.x;
+    h_f = hh.y;
+    if (fabs(h_i) >= 0.1 && s.alpha * h_i < 0.0) raise(c, LGAR_ST_NEG_POW);
+    if (fabs(h_f) >= 0.1 && s.alpha * h_f < 0.0) raise(c, LGAR_ST_NEG_POW);
+    dh = (h_f - h_i) / (double)nint;
+    k0 = k_from_se(se_i, s.ksat, s.m, s.inv_m, c);
+    st = c.st;
+  }
+  const int npl = (nint + 7) >> 3;
+  const int first = sub * npl + 1;
+  const int cnt = have ? max(0, min(npl, nint - first + 1)) : 0;
+  const double inv_nint = 1.0 / (double)nint;
+  double kk[GEFF_SPLIT_MAX_NODES];
+  double klast = 0.0;
+  int bad_first = 0;
+  double S = 0.0, Csei = 0.0, Ahi = 0.0, Ahf = 0.0, Ca = 0.0, Cn = 0.0, Cm = 0.0;
+  if (have && sub == 0) {  // node 0: K(Se_i), a direct function of Se_i
+    const NodeFull n0 = k_node_full(h_i, true, se_i, s.alpha, s.n, s.m, s.inv_m, s.ksat);
+    if (st == 0 && n0.bad) st = n0.bad;
+    S = 0.5 * k0;
+    Csei = 0.5 * n0.dk_se;
+    Cm = 0.5 * n0.dk_m;
+  }
+  if (cnt > 0) {
+    double h = geff_split_start(h_i, dh, first);
+#pragma unroll
+    for (int i = 0; i < GEFF_SPLIT_MAX_NODES; i += 2) {
+      kk[i] = kk[i + 1] = 0.0;
+      if (i < cnt) {
+        const double ha = h, hb = ha + dh;
+        h = hb + dh;
+        const NodeFull2 nf = k_node_full_x2(ha, hb, s.alpha, s.n, s.m, s.inv_m, s.ksat);
+        kk[i] = nf.K[0];
+        kk[i + 1] = nf.K[1];
+        klast = (i + 1 < cnt) ? nf.K[1] : nf.K[0];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          if (i + e < cnt) {
+            if (bad_first == 0 && nf.bad[e]) bad_first = nf.bad[e];
+            const int node = first + i + e;
+            const double wgt = (node == nint) ? 0.5 : 1.0;
+            const double frac = (double)node * inv_nint;
+            S += wgt * nf.K[e];
+            Ahi += wgt * nf.dk_h[e] * (1.0 - frac);
+            Ahf += wgt * nf.dk_h[e] * frac;
+            Ca += wgt * nf.dk_a[e];
+            Cn += wgt * nf.dk_n[e];
+            Cm += wgt * nf.dk_m[e];
+          }
+        }
+      }
+    }
+  }
+  double kin = __shfl_up_sync(FULL, klast, 1);
+  if (sub == 0) kin = k0;
+  const double half = dh / 2.0;
+  double acc = 0.0;
+#pragma unroll 1
+  for (int p = 0; p < 8; p++) {
+    if (sub == p && cnt > 0) {
+      double k1 = kin;
+#pragma unroll
+      for (int i = 0; i < GEFF_SPLIT_MAX_NODES; i++) {
+        if (i < cnt) {
+          acc = acc + ((k1 + kk[i]) * half);
+          k1 = kk[i];
+        }
+      }
+    }
+    acc = __shfl_sync(FULL, acc, base + p);
+    const int v = __shfl_sync(FULL, bad_first, base + p);
+    if (st == 0 && v) st = v;
+  }
+#pragma unroll
+  for (int d = 1; d < 8; d <<= 1) {  // sums over the eight sub-lanes of the group
+    S += __shfl_xor_sync(FULL, S, d);
+    Csei += __shfl_xor_sync(FULL, Csei, d);
+    Ahi += __shfl_xor_sync(FULL, Ahi, d);
+    Ahf += __shfl_xor_sync(FULL, Ahf, d);
+    Ca += __shfl_xor_sync(FULL, Ca, d);
+    Cn += __shfl_xor_sync(FULL, Cn, d);
+    Cm += __shfl_xor_sync(FULL, Cm, d);
+  }
+  if (have && sub == 0) {
+    const P4 pi = h_se_partials_core(se_i, s.alpha, s.ninv_m, s.inv_m, s.inv_n, h_i);
+    const P4 pf = h_se_partials_core(se_f, s.alpha, s.ninv_m, s.inv_m, s.inv_n, h_f);
+    const double G = dh * S;
+    const double sg = (G / s.ksat > 0.0) ? 1.0 : ((G / s.ksat < 0.0) ? -1.0 : 0.0);
+    const double f = sg / s.ksat;
+    const double dG_dhi = -S * inv_nint + dh * Ahi;
+    const double dG_dhf = S * inv_nint + dh * Ahf;
+    const double inv_span = 1.0 / (s.the - s.thr);
+    q->a[grp] = fabs(acc / s.ksat);
+    q->st[grp] = st;
+    double* dq = g_geffq_partials[threadIdx.x >> 5] + grp;
+    dq[0 * 32] = f * (dG_dhi * pi.a + dh * Csei) * inv_span;
+    dq[1 * 32] = f * (dG_dhf * pf.a) * inv_span;
+    dq[2 * 32] = f * (dh * Ca + dG_dhi * pi.b + dG_dhf * pf.b);
+    dq[3 * 32] = f * (dh * Cn + dG_dhi * pi.c + dG_dhf * pf.c);
+    dq[4 * 32] = f * (dh * Cm + dG_dhi * pi.d + dG_dhf * pf.d);
+  }
+  __syncwarp();
+}
+
 // ---- queue protocol shared by the three call sites of a sub-step ------------------------------------------------
 __device__ __forceinline__ void geffq_put(GeffQueue* q, int slot, int owner, int layer, double t1, double t2) {
   q->a[slot] = t1;
@@ -1213,12 +1432,17 @@ __device__ __forceinline__ Var geffq_get(GeffQueue* q, int slot, const Var& t1, 
   const double d[5] = {dq[0 * 32], dq[1 * 32], dq[2 * 32], dq[3 * 32], dq[4 * 32]};
   return tape_record_n(q->a[slot], 5, ids, d);
 }
-__device__ __forceinline__ void geffq_eval(GeffQueue* q, const SoilT<double>* soil, int L, int nint) {
-  geff_batch_eval(q, soil, L, nint);
+__device__ __forceinline__ void geffq_eval(GeffQueue* q, const SoilT<double>* soil, int L, int nint, bool split = false) {
+  if (split) geff_batch_eval_split(q, soil, L, nint);
+  else geff_batch_eval(q, soil, L, nint);
 }
-__device__ __forceinline__ void geffq_eval(GeffQueue* q, const SoilT<Var>* soil, int L, int nint) {
-  geff_batch_eval_taped(q, soil, L, nint);
+__device__ __forceinline__ void geffq_eval(GeffQueue* q, const SoilT<Var>* soil, int L, int nint, bool split = false) {
+  if (split) geff_batch_eval_split_taped(q, soil, L, nint);
+  else geff_batch_eval_taped(q, soil, L, nint);
 }
+// remainder rule of a phase: up to this many left-over requests go through split batches (4 per batch, ~1/7 of the
+// latency of a full batch each); more than that fill one full batch
+constexpr int GEFF_SPLIT_UP_TO = 20;
 
 // At most one request per lane (insert_water, calc_dry_depth): slot = lane.  Warp-convergent.
 template <int GM, class R>

@@ -339,8 +339,9 @@ __device__ void substep(Tile<FM, R>& T, bool act, double precip_rate, double pet
     int g = incl - nreq;   // queue index of this lane's next request
     int cur = 0;           // next front to look at
     int rem = nreq;
-    for (int lo = 0; lo < total; lo += 32) {
-      const int hi = lo + 32;
+    for (int lo = 0; lo < total;) {
+      const bool split = (total - lo) <= GEFF_SPLIT_UP_TO;  // warp-uniform
+      const int hi = lo + (split ? GEFF_SPLIT_SLOTS : 32);
       gq->meta[lane] = -1;
       __syncwarp();
       {
@@ -355,7 +356,7 @@ __device__ void substep(Tile<FM, R>& T, bool act, double precip_rate, double pet
         }
       }
       __syncwarp();
-      geffq_eval(gq, C.soil, K.p.num_layers, nint);
+      geffq_eval(gq, C.soil, K.p.num_layers, nint, split);
       while (rem > 0 && g < hi) {
         const int i = cur++;
         if (C.tb(i)) continue;
@@ -383,6 +384,7 @@ __device__ void substep(Tile<FM, R>& T, bool act, double precip_rate, double pet
         C.s(F_DZDT, i, dzdt);
       }
       __syncwarp();
+      lo = hi;
     }
     if (go && c.st == 0 && pre_err) raise(c, pre_err);
   } else

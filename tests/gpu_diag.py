@@ -15,6 +15,13 @@ for B, T in shapes:
             setattr(we, k, np.ascontiguousarray(getattr(we, k)[:, a:a + cnt]))
         we.site_index = np.ascontiguousarray(we.site_index[a:a + cnt])
         B = cnt
+    rep = os.environ.get("LGAR_DIAG_REPLICATE")
+    if rep:  # experiment: every warp works on a copy of the same 32 columns (tile `rep`): the warps of an SM then run in phase
+        k = int(rep)
+        idx = np.tile(np.arange(32 * k, 32 * k + 32), (B + 31) // 32)[:B]
+        for key in ("alpha", "n", "ksat", "theta_r", "theta_e", "thickness"):
+            setattr(we, key, np.ascontiguousarray(getattr(we, key)[:, idx]))
+        we.site_index = np.ascontiguousarray(we.site_index[idx])
     ens = ColumnEnsemble(theta_r=we.theta_r, theta_e=we.theta_e, thickness=we.thickness, forcing=we.forcing,
                          site_index=we.site_index, max_fronts=int(os.environ.get("LGAR_DIAG_FM", "16")),
                          chunk_steps=int(os.environ.get("LGAR_DIAG_CHUNK", "64")))
@@ -42,5 +49,7 @@ for B, T in shapes:
     tc = res.tile_cycles.cpu().numpy(); top = np.argsort(-tc)[:4]
     print(f"  tile busy time: sum {tc.sum() / 1.965e9:.1f} s = {tc.sum() / 1.965e9 / 1184:.3f} s per resident warp (1184), "
           f"max {tc.max() / 1.965e9:.3f} s, mean {tc.mean() / 1.965e9:.4f} s, p99 {np.percentile(tc, 99) / 1.965e9:.3f} s", flush=True)
+    if os.environ.get("LGAR_DIAG_TILES"):
+        print("  tiles", {int(k): round(float(tc[int(k)]) / 1.965e9, 4) for k in os.environ["LGAR_DIAG_TILES"].split(",")}, flush=True)
     print("  slowest tiles:", [(int(i), round(float(tc[i]) / 1.9e9, 2)) for i in top], "median tile s", round(float(np.median(tc)) / 1.9e9, 3), flush=True)
     print(f"B={B} T={T}: first {dt:.3f}s, best of {len(times)} passes {kms:.1f} ms (all: {[round(x) for x in times]}) -> {alive/kms*1e3:.4g} col-steps/s  alive col-steps={alive}  status hist={np.bincount(st, minlength=9).tolist()} counters={res.counters.cpu().numpy().tolist()}", flush=True)
