@@ -1010,7 +1010,7 @@ __device__ __noinline__ void geff_batch_eval(GeffQueue* q, const ST* soil, int L
       const double ha = h2, hb = ha + dh;
       h2 = hb + dh;
       int bad;
-      const double2 kk = k_nodes_core_x2(ha, hb, s.alpha, s.n, s.m, s.inv_m, s.ksat, &bad);
+      const double2 kk = k_nodes_core_x2(ha, (i + 1 < nint) ? hb : ha, s.alpha, s.n, s.m, s.inv_m, s.ksat, &bad);
       geff = geff + ((k1 + kk.x) * half);
       k1 = kk.x;
       if (i + 1 < nint) {
@@ -1145,7 +1145,7 @@ __device__ __noinline__ void geff_batch_eval_taped(GeffQueue* q, const ST* soil,
     for (int i = 0; i < nint; i += 2) {
       const double ha = h2, hb = ha + dh;
       h2 = hb + dh;
-      const NodeFull2 nf = k_node_full_x2(ha, hb, s.alpha, s.n, s.m, s.inv_m, s.ksat);
+      const NodeFull2 nf = k_node_full_x2(ha, (i + 1 < nint) ? hb : ha, s.alpha, s.n, s.m, s.inv_m, s.ksat);
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         const int node = i + e + 1;
@@ -1183,6 +1183,10 @@ __device__ __noinline__ void geff_batch_eval_taped(GeffQueue* q, const ST* soil,
   __syncwarp();
 }
 
+#ifndef LGAR_GEFF_SPLIT_UP_TO
+#define LGAR_GEFF_SPLIT_UP_TO 0
+#endif
+#if LGAR_GEFF_SPLIT_UP_TO > 0
 // ------------------------------------------------------------------------------------
 // Split batches: EIGHT lanes per request, at most four requests per batch.  A full batch costs the latency of one
 // whole request (~480 dependent pows) however many of its 32 slots are filled, so the remainder of a phase's
@@ -1191,6 +1195,10 @@ __device__ __noinline__ void geff_batch_eval_taped(GeffQueue* q, const ST* soil,
 // the reference) come from advance_rounded(); the trapezoid terms stay in registers, and the closing sum -- which
 // must be added up in the reference's order to give the same bits -- is handed from sub-lane to sub-lane.
 // Latency: 60 pows + 120 dependent adds instead of 480 pows.  Values are bit-identical to the full batch.
+// MEASURED SLOWER and therefore compiled out by default (-DLGAR_GEFF_SPLIT_UP_TO=8 enables it): 933 ms against 866 ms
+// at 125,000 x 640 -- the fixed part of a batch (soil gather, end points, six pows, the hand-over of the sum) and the
+// extra code in the instruction cache outweigh the shorter node loop; with it the gradients also depend on the
+// placement in the last bits (different summation order of the partials in split and full batches).
 // ------------------------------------------------------------------------------------
 constexpr int GEFF_SPLIT_SLOTS = 4;
 constexpr int GEFF_SPLIT_MAX_NODES = 16;  // per sub-lane (nint <= 128)
@@ -1242,7 +1250,9 @@ __device__ __noinline__ void geff_batch_eval_split(GeffQueue* q, const ST* soil,
         const double ha = h, hb = ha + dh;
         h = hb + dh;
         int bad;
-        const double2 k2 = k_nodes_core_x2(ha, hb, s.alpha, s.n, s.m, s.inv_m, s.ksat, &bad);
+        // (an odd share ends with half a pair: the second element repeats the first, so that no abscissa beyond the
+        // request's range is ever evaluated and `bad` only reflects real nodes)
+        const double2 k2 = k_nodes_core_x2(ha, (i + 1 < cnt) ? hb : ha, s.alpha, s.n, s.m, s.inv_m, s.ksat, &bad);
         kk[i] = k2.x;
         kk[i + 1] = k2.y;
         klast = (i + 1 < cnt) ? k2.y : k2.x;
@@ -1329,7 +1339,7 @@ __device__ __noinline__ void geff_batch_eval_split_taped(GeffQueue* q, const ST*
       if (i < cnt) {
         const double ha = h, hb = ha + dh;
         h = hb + dh;
-        const NodeFull2 nf = k_node_full_x2(ha, hb, s.alpha, s.n, s.m, s.inv_m, s.ksat);
+        const NodeFull2 nf = k_node_full_x2(ha, (i + 1 < cnt) ? hb : ha, s.alpha, s.n, s.m, s.inv_m, s.ksat);
         kk[i] = nf.K[0];
         kk[i + 1] = nf.K[1];
         klast = (i + 1 < cnt) ? nf.K[1] : nf.K[0];
@@ -1402,6 +1412,8 @@ __device__ __noinline__ void geff_batch_eval_split_taped(GeffQueue* q, const ST*
   __syncwarp();
 }
 
+#endif  // LGAR_GEFF_SPLIT_UP_TO > 0
+
 // ---- queue protocol shared by the three call sites of a sub-step ------------------------------------------------
 __device__ __forceinline__ void geffq_put(GeffQueue* q, int slot, int owner, int layer, double t1, double t2) {
   q->a[slot] = t1;
@@ -1433,16 +1445,31 @@ __device__ __forceinline__ Var geffq_get(GeffQueue* q, int slot, const Var& t1, 
   return tape_record_n(q->a[slot], 5, ids, d);
 }
 __device__ __forceinline__ void geffq_eval(GeffQueue* q, const SoilT<double>* soil, int L, int nint, bool split = false) {
-  if (split) geff_batch_eval_split(q, soil, L, nint);
-  else geff_batch_eval(q, soil, L, nint);
+#if LGAR_GEFF_SPLIT_UP_TO > 0
+  if (split) {
+    geff_batch_eval_split(q, soil, L, nint);
+    return;
+  }
+#endif
+  (void)split;
+  geff_batch_eval(q, soil, L, nint);
 }
 __device__ __forceinline__ void geffq_eval(GeffQueue* q, const SoilT<Var>* soil, int L, int nint, bool split = false) {
-  if (split) geff_batch_eval_split_taped(q, soil, L, nint);
-  else geff_batch_eval_taped(q, soil, L, nint);
+#if LGAR_GEFF_SPLIT_UP_TO > 0
+  if (split) {
+    geff_batch_eval_split_taped(q, soil, L, nint);
+    return;
+  }
+#endif
+  (void)split;
+  geff_batch_eval_taped(q, soil, L, nint);
 }
 // remainder rule of a phase: up to this many left-over requests go through split batches (4 per batch, ~1/7 of the
 // latency of a full batch each); more than that fill one full batch
-constexpr int GEFF_SPLIT_UP_TO = 20;
+constexpr int GEFF_SPLIT_UP_TO = LGAR_GEFF_SPLIT_UP_TO;
+#if LGAR_GEFF_SPLIT_UP_TO == 0
+constexpr int GEFF_SPLIT_SLOTS = 4;
+#endif
 
 // At most one request per lane (insert_water, calc_dry_depth): slot = lane.  Warp-convergent.
 template <int GM, class R>
