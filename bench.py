@@ -432,15 +432,26 @@ def main():
     parity = None
     if cpu:
         _, _, r_c, ncol, _ = cpu
-        st_mis = int((r_c["status"] != status[:ncol]).sum())
+        ITER_CAP = lgar_b200.STATUS_NAMES.index("ITER_CAP")
+        g_st, o_st = status[:ncol], r_c["status"]
+        # ITER_CAP is a limit of the two IMPLEMENTATIONS (the reference would keep iterating): the oracle counts literal
+        # iterations, the CUDA root finder crosses long runs in exact jumps and may finish a search the oracle cuts off.
+        # Such columns are not comparable and are listed separately.
+        capped = (g_st == ITER_CAP) | (o_st == ITER_CAP)
+        cmp_ = ~capped
         cr = np.where(crash[:ncol] <= -2, -2 - crash[:ncol], crash[:ncol])
-        cr_mis = int(((r_c["status"] != 0) & (r_c["crash_step"] != cr)).sum())
-        ok = (r_c["status"] == 0) & (status[:ncol] == 0)
+        st_bad = np.nonzero(cmp_ & (o_st != g_st))[0]
+        cr_bad = np.nonzero(cmp_ & (o_st != 0) & (o_st == g_st) & (r_c["crash_step"] != cr))[0]
+        ok = cmp_ & (o_st == 0) & (g_st == 0)
         g, o = sums[:, :ncol].T[ok], r_c["sums"][ok]
         excess = float(np.max(np.abs(g - o) / (1e-10 + 1e-9 * np.abs(o)), initial=0.0))
-        parity = {"columns": int(ncol), "ok_columns": int(ok.sum()), "status_mismatches": st_mis,
-                  "crash_step_mismatches": cr_mis, "max_excess": excess,
-                  "what": "full-record sums of all 10 outputs vs the CPU oracle, tolerance 1e-9 rel + 1e-10 abs (max_excess <= 1 passes)"}
+        parity = {"columns": int(ncol), "ok_columns": int(ok.sum()), "status_mismatches": int(len(st_bad)),
+                  "crash_step_mismatches": int(len(cr_bad)), "max_excess": excess,
+                  "iter_cap_columns_not_compared": int(capped.sum()),
+                  "mismatching_columns": [{"column": int(b), "gpu": [int(g_st[b]), int(cr[b])], "oracle": [int(o_st[b]), int(r_c["crash_step"][b])]}
+                                          for b in list(st_bad[:4]) + list(cr_bad[:4])],
+                  "what": "full-record sums of all 10 outputs, status and crash step vs the CPU oracle; tolerance 1e-9 rel + 1e-10 abs "
+                          "(max_excess <= 1 passes)"}
 
     # ---- e2e: host tensors in, results out, through the public API, segment by segment ----------------------------
     e2e = None

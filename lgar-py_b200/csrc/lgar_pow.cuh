@@ -8,6 +8,14 @@
 // latency on B200 (tools/fp64_microbench.cu); this routine needs ~55 FP64 operations, two small
 // table look-ups (6 KB, L1-resident), and inlines so that independent evaluations overlap.
 //
+// Lineage: the structure is that of the pow in glibc >= 2.28 / ARM Optimized Routines (Szabolcs Nagy, `pow.c` +
+// `pow_log_data.c` / `exp_data.c`: 128-entry `invc / logc / logctail` table indexed by the leading mantissa bits,
+// log1p polynomial on the exact residual r, `tail`-corrected 2^(k/128) table with `sbits` exponent reconstruction) --
+// i.e. the very routine the reference's torch.pow ends up in on the CPU, which is why its accuracy class is the
+// target.  No code or table was copied: the interval layout, polynomial degrees and error handling are written for
+// this kernel (fast path only, specials delegated) and all tables and coefficients are generated here with mpmath
+// (tools/gen_pow_tables.py).
+//
 // Algorithm (tables from tools/gen_pow_tables.py, mpmath 200 bit):
 //   log:  x = 2^k z; i = sub-interval of z (128 in mantissa-bit space, 1.0 at the centre of
 //         interval 64); r = z*invc_i - 1 as an exact two-term sum (p = fl(z*invc), e = fma error);
