@@ -208,6 +208,16 @@ __global__ void __launch_bounds__(NT, 2) lgar_backward_kernel(const BParams P) {
       const int t1 = min(Tn, t0 + K.chunk_steps);
       // ---- forward through the chunk ON THE TAPE, from the checkpoint the forward kernel stored
       load_state(K, chunk, slot_cc, Tv);
+      if (K.slog) {  // end points of the root finders, logged by the forward pass
+        C.logp = K.slog + (size_t)chunk * K.slog_cap * K.Bp + slot_cc;
+        C.log_pos = 0;
+        C.log_valid = valid ? min(__ldcg(K.slog_count + (size_t)chunk * K.Bp + slot_cc), K.slog_cap) : 0;
+        C.log_mode = 2;
+        C.log_stride = K.Bp;
+      } else {
+        C.logp = nullptr;
+        C.log_pos = C.log_valid = C.log_mode = C.log_stride = 0;
+      }
       int arena_used = 0;
       for (int t = t0; t < t1; t++) {
         const double2 x = __ldg(reinterpret_cast<const double2*>(frc) + t);

@@ -68,8 +68,12 @@ int shape_of(const lgar_problem* p, Shape& s) {
 size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct Carve {
-  size_t off_d, off_i, off_f, off_done, off_item, total;
+  size_t off_d, off_i, off_f, off_slog, off_slogc, off_done, off_item, total;
+  int slog_cap;
 };
+// search log of the reverse pass (KParams::slog): average budget of entries per sub-step and lane; a lane that needs
+// more in some chunk searches again from there on (correct, just slower)
+#define LGAR_SLOG_AVG 5
 
 Carve carve(const Shape& s, int with_grad) {
   const size_t nck = with_grad ? (size_t)s.nchunks + 1 : 1;
@@ -79,6 +83,9 @@ Carve carve(const Shape& s, int with_grad) {
   c.off_d = o;   o = align_up(o + nck * nd * s.Bp * sizeof(double));
   c.off_i = o;   o = align_up(o + nck * lgar::NI_STATE * s.Bp * sizeof(int32_t));
   c.off_f = o;   o = align_up(o + nck * (size_t)s.FM * s.Bp);
+  c.slog_cap = with_grad ? s.chunk * s.S * LGAR_SLOG_AVG : 0;
+  c.off_slog = o;  o = align_up(o + (with_grad ? (size_t)s.nchunks * c.slog_cap * s.Bp * sizeof(double) : 0));
+  c.off_slogc = o; o = align_up(o + (with_grad ? (size_t)s.nchunks * s.Bp * sizeof(int32_t) : 0));
   c.off_done = o; o = align_up(o + (size_t)s.ntiles * sizeof(int32_t));
   c.off_item = o; o = align_up(o + 64);
   c.total = o;
@@ -107,7 +114,7 @@ static int tape_cap() {
 int backward_ctas_per_sm(const Shape&) { return 2; }  // __launch_bounds__(NT, 2) of lgar_backward_kernel
 // tape arena of one chunk: average budget of LGAR_TAPE_AVG entries per sub-step (a sub-step may use up to
 // LGAR_TAPE_CAP); exhaustion flags the column (NaN gradient + tape_overflow)
-#define LGAR_TAPE_AVG 640
+#define LGAR_TAPE_AVG 320  /* measured on the bench ensemble: 83 entries per sub-step on average */
 int backward_arena_cap(const Shape& s) {
   long long c = (long long)s.chunk * s.S * LGAR_TAPE_AVG;  // chunk * S <= 512 (checked): fits an int
   if (std::getenv("LGAR_DEBUG_TAPE_CAP")) c = LGAR_TAPE_CAP;
@@ -300,6 +307,11 @@ int lgar_forward(const lgar_problem* p, const lgar_outputs* out, void* workspace
   K.t_begin = s.t_begin;
   K.t_end = s.t_end;
   K.keep_ckpt = keep_checkpoints ? 1 : 0;
+  if (keep_checkpoints) {
+    K.slog = (double*)(w + c.off_slog);
+    K.slog_count = (int32_t*)(w + c.off_slogc);
+    K.slog_cap = c.slog_cap;
+  }
   K.iter_cap = p->iter_cap > 0 ? p->iter_cap : 1000000;
   if (p->pipeline_seq <= 1) {  // (a memset between two kernels of a pipelined sequence would serialise them)
     if (out->counters) CUDA_TRY(cudaMemsetAsync(out->counters, 0, 16 * sizeof(unsigned long long), st));
@@ -359,6 +371,9 @@ int lgar_backward_ex(const lgar_problem* p, const lgar_gradients* g, void* works
   K.t_end = s.T;
   if (s.t_begin != 0 || s.t_end != s.T) return fail(LGAR_E_INVALID, "lgar_backward needs the whole record (no step window)");
   K.keep_ckpt = 1;
+  K.slog = std::getenv("LGAR_DEBUG_NO_SEARCH_LOG") ? nullptr : (double*)(w + c.off_slog);
+  K.slog_count = (int32_t*)(w + c.off_slogc);
+  K.slog_cap = c.slog_cap;
   K.iter_cap = p->iter_cap > 0 ? p->iter_cap : 1000000;
   P.grad_per_step = g->grad_per_step;
   P.grad_mask = g->grad_per_step ? g->grad_mask : 0;

@@ -1512,6 +1512,34 @@ struct Column {
   double previous_precip;
   R giuh[NGIUH];
   bool empty_list;   // set by mass_balance() when a layer list is empty (IndexError in the reference)
+  // Search log (reverse pass): the two root finders of a sub-step (Layer.theta_mass_balance, Layer.check_column_mass)
+  // only STEER psi / the depth by constants -- they never appear on the tape (Q14) -- so the forward kernel, when it
+  // stores checkpoints, also logs where every search ended (one double per search, per lane and chunk, in program
+  // order) and the taped recompute of the reverse kernel reads the end point instead of searching again: no
+  // upper-layer sums (P1), no iterations (P2).  A lane whose log is exhausted searches as usual.
+  double* logp;      // this lane's log of the current chunk: entry k at logp[k * log_stride]; nullptr = no log
+  int log_pos;       // entries written / consumed so far
+  int log_valid;     // write mode: capacity; read mode: entries the forward pass stored (<= capacity)
+  int log_mode;      // 0 off, 1 write (forward with checkpoints), 2 read (taped recompute)
+  int log_stride;
+
+  static constexpr unsigned long long LOG_NAN = 0x7ff8000000000000ULL;
+  enum LogMark { LOG_SINGLE = 1, LOG_NONE = 2, LOG_SCALE = 16 };
+  __device__ __forceinline__ void log_put(double v) {
+    if (log_pos < log_valid) logp[(size_t)log_pos * log_stride] = v;
+    log_pos++;
+  }
+  __device__ __forceinline__ void log_put_mark(int mark) { log_put(__longlong_as_double((long long)(LOG_NAN | (unsigned)mark))); }
+  __device__ __forceinline__ bool log_get(double& v) {
+    if (log_pos >= log_valid) {
+      log_pos = 0x40000000;  // exhausted: search from here on (and never come back to the log of this chunk)
+      log_valid = 0;
+      return false;
+    }
+    v = __ldcg(logp + (size_t)log_pos * log_stride);
+    log_pos++;
+    return true;
+  }
 
   __device__ __forceinline__ double& f(int fld, int i) { return fb[(fld * FM + i) * NT]; }
   __device__ __forceinline__ short& fid(int fld, int i) { return ib[(fld * FM + i) * NT]; }
@@ -1651,6 +1679,13 @@ struct Column {
       long long it = 0;
       int run_len = 0;
       bool run_up = false;
+      if (log_mode == 2 && fabs(err - 1e-12) > 1e-12) {  // the forward pass logged where this search ended
+        double v;
+        if (log_get(v)) {
+          f(F_DEPTH, fd) = v;
+          return;
+        }
+      }
       while (fabs(err - 1e-12) > 1e-12) {
         if (++it > c.iter_cap) {
           raise(c, LGAR_ST_ITER_CAP);
@@ -1707,6 +1742,7 @@ struct Column {
           f(F_DEPTH, fd) = depth_new;
         }
       }
+      if (log_mode == 1 && it > 0) log_put(depth_new);
     }
   }
 
@@ -1816,6 +1852,26 @@ struct Column {
           add_flux = (lay(fd) == l);
         }
       }
+      // ---- search log (taped recompute): the end point of this front's search, if the forward pass logged it
+      bool log_hit = false, log_single = false, log_have = false;
+      double log_psi = 0.0, log_scale = 1.0;
+      if (log_mode == 2 && mine && kind >= K_INLAYER_DEEP && c.st == 0) {
+        double v;
+        if (log_get(v)) {
+          int mark = isnan(v) ? (int)((unsigned long long)__double_as_longlong(v) & 0xffffULL) : 0;
+          if (mark >= LOG_SCALE) {  // psi was scaled by 0.1^k on the way (the `psi < 0` guard): same product chain
+            for (int k = LOG_SCALE; k < mark; k++) log_scale = log_scale * 0.1;
+            log_get(v);
+            mark = 0;
+          }
+          log_hit = true;
+          log_single = (mark == LOG_SINGLE);
+          log_have = (mark == 0);
+          log_psi = v;
+          nup = 0;  // no upper-layer sums, no iterations for this lane
+          add_flux = false;
+        }
+      }
       // ---- P1: sums over the layers above (convergent, values only)
       double dth[MAXL - 1], dtk[MAXL - 1];
       int nupmax = nup;
@@ -1860,8 +1916,13 @@ struct Column {
       bool have_theta = false;  // theta already holds theta_l(psi_cm) (value)
       const bool wants = mine && (kind == K_DEEPEST || kind >= K_INLAYER_DEEP) && (c.st == 0);
       // early return `delta_mass <= tolerance` (and the deepest-front case): one evaluation
-      const bool single = wants && (kind == K_DEEPEST || delta_mass <= tol);
-      bool active = wants && kind >= K_INLAYER_DEEP && (delta_mass > tol);
+      const bool single = wants && (kind == K_DEEPEST || (log_hit ? log_single : (delta_mass <= tol)));
+      bool active = wants && kind >= K_INLAYER_DEEP && !log_hit && (delta_mass > tol);
+      if (log_hit && log_have) {
+        psi_cm = log_psi;
+        psi_scale = log_scale;
+        have_theta = true;
+      }
       {
         bool switched = false;
         double factor = 1.0;
@@ -2028,6 +2089,17 @@ struct Column {
             }
           }
         }
+      }
+      if (log_mode == 1 && wants && kind >= K_INLAYER_DEEP) {  // forward with checkpoints: log the end point
+        if (single) log_put_mark(LOG_SINGLE);
+        else if (have_theta) {
+          if (psi_scale != 1.0) {
+            int k = 0;
+            for (double sc = 1.0; sc != psi_scale && k < 300; k++) sc = sc * 0.1;
+            log_put_mark(LOG_SCALE + k);
+          }
+          log_put(psi_cm);
+        } else log_put_mark(LOG_NONE);
       }
       // ---- P3: theta = theta_l(psi_final) on the tape, psi = h(Se(theta)) tail
       if (mine && c.st == 0 && (kind == K_DEEPEST || kind >= K_INLAYER_DEEP)) {

@@ -47,6 +47,9 @@ struct KParams {
   // leaves.  `overlap`: the previous window may still be running, so even the first chunk of a tile waits for the
   // tile's progress counter.
   int32_t seq, slot, overlap;
+  double* slog;          // search log [nchunks][slog_cap][Bp] (only with keep_ckpt; see Column::logp), nullptr = none
+  int32_t* slog_count;   // [nchunks][Bp] entries the forward pass produced per lane and chunk
+  int32_t slog_cap;
   int32_t time_phases;   // reverse kernel diagnostics: accumulate the phase timers of substep() in Ctx::ph
   int32_t keep_ckpt;     // 1: state of chunk c is stored at index c (+ final at nchunks)
   long long iter_cap;
@@ -611,6 +614,8 @@ __global__ void __launch_bounds__(NT, (FM == 32) ? 1 : ((FM == 16) ? 2 : ((FM ==
   T.col.ib = nullptr;
   T.col.gb = sm_flags + threadIdx.x;
   T.ctx.iter_cap = K.iter_cap;
+  T.col.logp = nullptr;
+  T.col.log_pos = T.col.log_valid = T.col.log_mode = T.col.log_stride = 0;
 
   for (;;) {
     if (lane == 0) {
@@ -681,6 +686,13 @@ __global__ void __launch_bounds__(NT, (FM == 32) ? 1 : ((FM == 16) ? 2 : ((FM ==
       load_state(K, slot_in, slot_cc, T);
     }
     precompute_psi_wp(T, p.wilting_point_psi);
+    if (K.slog && K.keep_ckpt) {  // log the end points of the root finders for the reverse pass
+      T.col.logp = K.slog + (size_t)chunk * K.slog_cap * K.Bp + slot_cc;
+      T.col.log_pos = 0;
+      T.col.log_valid = valid ? K.slog_cap : 0;
+      T.col.log_mode = 1;
+      T.col.log_stride = K.Bp;
+    }
     const int site = (p.site_index && valid) ? __ldg(p.site_index + b) : 0;
     const double* frc = p.forcing + (size_t)site * Tn * 2;
     // one forcing record for the whole warp?  (lanes beyond B follow lane 0)
@@ -741,6 +753,7 @@ __global__ void __launch_bounds__(NT, (FM == 32) ? 1 : ((FM == 16) ? 2 : ((FM ==
     // publish the state for the next chunk of this tile (release)
     const int slot_out = K.keep_ckpt ? chunk + 1 : 0;
     if (valid) save_state(K, slot_out, slot_c, T);
+    if (T.col.log_mode == 1 && valid) K.slog_count[(size_t)chunk * K.Bp + slot_c] = T.col.log_pos;
     if (chunk == K.nchunks - 1 && valid) {
       if (K.o.sums) {
 #pragma unroll
