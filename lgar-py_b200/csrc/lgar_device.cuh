@@ -79,13 +79,14 @@ __device__ __noinline__ double pow_f64(double a, double b) {
   const double r = pow_core(a, b, ok);  // lgar_pow.cuh: ~0.50 ulp
   return ok ? r : pow_slow(a, b);
 }
+__device__ __noinline__ double2 pow_log_slow(double a, double b) { return make_double2(pow(a, b), log(a)); }  // cold
 // a^b together with log(a) (by-product of the pow core): derivative weights of the reverse kernel
 __device__ __noinline__ double2 pow_log_f64(double a, double b) {
   const double xv[1] = {a}, yv[1] = {b};
   double r[1], lg[1];
   bool ok[1];
   pow_core_v<1>(xv, yv, r, ok, lg);
-  if (!ok[0]) return make_double2(pow_slow(a, b), log(a));
+  if (!ok[0]) return pow_log_slow(a, b);
   return make_double2(r[0], lg[0]);
 }
 // two INDEPENDENT pows issued interleaved from one basic block (ILP: pow is one long dependent chain)
@@ -117,8 +118,8 @@ __device__ __noinline__ D4 pow_log_x2(double x0, double y0, double x1, double y1
   double r[2], lg[2];
   bool ok[2];
   pow_core_v<2>(xv, yv, r, ok, lg);
-  if (!ok[0]) { r[0] = pow_slow(x0, y0); lg[0] = log(x0); }
-  if (!ok[1]) { r[1] = pow_slow(x1, y1); lg[1] = log(x1); }
+  if (!ok[0]) { const double2 q = pow_log_slow(x0, y0); r[0] = q.x; lg[0] = q.y; }  // (out of line: the hot loop of the
+  if (!ok[1]) { const double2 q = pow_log_slow(x1, y1); r[1] = q.x; lg[1] = q.y; }  // taped Geff stays small)
   D4 o;
   o.a = r[0]; o.b = lg[0]; o.c = r[1]; o.d = lg[1];
   return o;
