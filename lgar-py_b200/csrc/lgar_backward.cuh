@@ -140,12 +140,12 @@ __global__ void __launch_bounds__(NT, 2) lgar_backward_kernel(const BParams P) {
   if (lane == 0) g_geffq_partials[warp] = P.adj + (size_t)slot * (NL + P.step_cap) * 32;
   __syncwarp();
 
-  Tile<FM, Var> Tv;
+  Tile<FM, Var, 2> Tv;
   Tv.col.fb = sm_fields + threadIdx.x;
   Tv.col.ib = sm_ids + threadIdx.x;
   Tv.col.gb = sm_flags + threadIdx.x;
   Tv.ctx.iter_cap = K.iter_cap;
-  Column<FM, Var>& C = Tv.col;
+  Column<FM, Var, 2>& C = Tv.col;
   const unsigned long long nitems = (unsigned long long)K.ntiles * K.nchunks;
 
   for (;;) {
@@ -212,11 +212,10 @@ __global__ void __launch_bounds__(NT, 2) lgar_backward_kernel(const BParams P) {
         C.logp = K.slog + (size_t)chunk * K.slog_cap * K.Bp + slot_cc;
         C.log_pos = 0;
         C.log_valid = valid ? min(__ldcg(K.slog_count + (size_t)chunk * K.Bp + slot_cc), K.slog_cap) : 0;
-        C.log_mode = 2;
         C.log_stride = K.Bp;
       } else {
         C.logp = nullptr;
-        C.log_pos = C.log_valid = C.log_mode = C.log_stride = 0;
+        C.log_pos = C.log_valid = C.log_stride = 0;
       }
       int arena_used = 0;
       for (int t = t0; t < t1; t++) {

@@ -146,10 +146,10 @@ struct Plan {
   bool counters_reset;
 };
 
-template <int FM, bool COUNT, bool DUMP>
+template <int FM, bool COUNT, bool DUMP, bool LOGW = false>
 int launch_forward(Plan& P, cudaStream_t st) {
   lgar::KParams& K = P.K;
-  auto kern = lgar::lgar_forward_kernel<FM, COUNT, DUMP>;
+  auto kern = lgar::lgar_forward_kernel<FM, COUNT, DUMP, LOGW>;
   const size_t smem = smem_bytes<FM>();
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
@@ -307,10 +307,14 @@ int lgar_forward(const lgar_problem* p, const lgar_outputs* out, void* workspace
   K.t_begin = s.t_begin;
   K.t_end = s.t_end;
   K.keep_ckpt = keep_checkpoints ? 1 : 0;
+  // the search log is written by the default instantiation only (16 fronts, no counters); other configurations
+  // leave it empty (slog_count = 0) and the reverse pass searches again
+  const bool logw = keep_checkpoints && s.FM == 16 && !out->counters && !out->fronts && !p->use_closed_form_G;
   if (keep_checkpoints) {
     K.slog = (double*)(w + c.off_slog);
     K.slog_count = (int32_t*)(w + c.off_slogc);
     K.slog_cap = c.slog_cap;
+    if (!logw) CUDA_TRY(cudaMemsetAsync(K.slog_count, 0, (size_t)s.nchunks * s.Bp * sizeof(int32_t), st));
   }
   K.iter_cap = p->iter_cap > 0 ? p->iter_cap : 1000000;
   if (p->pipeline_seq <= 1) {  // (a memset between two kernels of a pipelined sequence would serialise them)
@@ -329,6 +333,7 @@ int lgar_forward(const lgar_problem* p, const lgar_outputs* out, void* workspace
   else if (s.FM == 8) { LGAR_DISPATCH(8) }
   else if (s.FM == 12) { LGAR_DISPATCH(12) }
   else if (s.FM == 32) rc = launch_forward<32, true, false>(plan, st);  // large-capacity fallback (1 CTA per SM)
+  else if (logw) rc = launch_forward<16, false, false, true>(plan, st);
   else { LGAR_DISPATCH(16) }
 #undef LGAR_DISPATCH
   return rc;

@@ -1495,7 +1495,7 @@ __device__ __forceinline__ R geff_one_per_lane(bool need, const R& theta_1, cons
 // R = double: forward kernel.  R = Var: taped pass (values in the same shared-memory array, tape
 // ids of the five fields in a parallel int array).
 // ------------------------------------------------------------------------------------
-template <int FM, class R>
+template <int FM, class R, int LM = 0>
 struct Column {
   static constexpr bool TAPED = !std::is_same<R, double>::value;
   double* fb;        // this thread's slot in the field array
@@ -1521,7 +1521,8 @@ struct Column {
   double* logp;      // this lane's log of the current chunk: entry k at logp[k * log_stride]; nullptr = no log
   int log_pos;       // entries written / consumed so far
   int log_valid;     // write mode: capacity; read mode: entries the forward pass stored (<= capacity)
-  int log_mode;      // 0 off, 1 write (forward with checkpoints), 2 read (taped recompute)
+  static constexpr int log_mode = LM;  // 0 off (production forward: compiled out), 1 write (forward with checkpoints),
+                                       // 2 read (taped recompute)
   int log_stride;
 
   static constexpr unsigned long long LOG_NAN = 0x7ff8000000000000ULL;

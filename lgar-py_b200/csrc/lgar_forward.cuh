@@ -55,9 +55,9 @@ struct KParams {
   long long iter_cap;
 };
 
-template <int FM, class R>
+template <int FM, class R, int LM = 0>
 struct Tile {
-  Column<FM, R> col;
+  Column<FM, R, LM> col;
   Ctx ctx;
   R acc[NOUT];        // per-forcing-step accumulators (reset every step)
   double sums[NOUT];  // running sums over time
@@ -66,8 +66,8 @@ struct Tile {
 };
 
 // ---- Layer.calc_aet (Layer.py:760-783) -> calc_aet (lgar/aet.py:17-51)
-template <int FM, class R>
-__device__ __forceinline__ void precompute_psi_wp(Tile<FM, R>& T, double wilting_psi) {
+template <int FM, class R, int LM>
+__device__ __forceinline__ void precompute_psi_wp(Tile<FM, R, LM>& T, double wilting_psi) {
   Ctx cc = T.ctx;
   cc.st = 0;
   const SoilT<R>& s = T.col.soil[0];
@@ -80,8 +80,8 @@ __device__ __forceinline__ void precompute_psi_wp(Tile<FM, R>& T, double wilting
 }
 __device__ __forceinline__ double pow3R(double x, Ctx& c) { return safe_pow(x, 3.0, c); }
 __device__ __forceinline__ Var pow3R(const Var& x, Ctx& c) { return pow3_(x, safe_pow(x.v, 3.0, c)); }
-template <int FM, class R>
-__device__ __forceinline__ R calc_aet(Tile<FM, R>& T, double pet, double dt) {
+template <int FM, class R, int LM>
+__device__ __forceinline__ R calc_aet(Tile<FM, R, LM>& T, double pet, double dt) {
   Ctx& c = T.ctx;
   if (T.psiwp_st) raise(c, T.psiwp_st);
   c.cnt[C_THETA_H] += 1;
@@ -93,9 +93,9 @@ __device__ __forceinline__ R calc_aet(Tile<FM, R>& T, double pet, double dt) {
 
 // set_internal_states (models/dpLGAR.py:97-147), Layer.__init__ (Layer.py:22-90),
 // WettingFront.__init__ (WettingFront.py:18-49), generate_soil_metrics (data/utils.py:40-105)
-template <int FM, class R>
-__device__ void init_column(Tile<FM, R>& T, double initial_psi, bool closed_form_G = false) {
-  Column<FM, R>& C = T.col;
+template <int FM, class R, int LM>
+__device__ void init_column(Tile<FM, R, LM>& T, double initial_psi, bool closed_form_G = false) {
+  Column<FM, R, LM>& C = T.col;
   Ctx& c = T.ctx;
   C.n = 0;
   C.cntpk = 0;
@@ -123,10 +123,10 @@ __device__ void init_column(Tile<FM, R>& T, double initial_psi, bool closed_form
 
 // ---- one sub-step: models/dpLGAR.py:176-298.  Warp-convergent: every lane of the warp calls it;
 //      lanes with act == false only take part in the cooperative Geff evaluations.
-template <int FM, class R, int GM>
-__device__ void substep(Tile<FM, R>& T, bool act, double precip_rate, double pet_rate, const KParams& K,
+template <int FM, class R, int GM, int LM>
+__device__ void substep(Tile<FM, R, LM>& T, bool act, double precip_rate, double pet_rate, const KParams& K,
                         double* nodebuf) {
-  Column<FM, R>& C = T.col;
+  Column<FM, R, LM>& C = T.col;
   Ctx& c = T.ctx;
   const double dt = K.p.subcycle_length_h;
   const int nint = (GM == 2 && K.p.use_closed_form_G) ? -1 : K.p.nint;  // nint < 0 selects the closed-form Geff (geff_warpR)
@@ -467,11 +467,11 @@ __device__ void substep(Tile<FM, R>& T, bool act, double precip_rate, double pet
 // state save / restore (global memory, column fastest).  Loads bypass L1 (__ldcg): the
 // record may have been written by a warp on another SM.
 // ------------------------------------------------------------------------------------
-template <int FM, class R>
-__device__ void save_state(const KParams& K, int slot, int b, Tile<FM, R>& T) {
+template <int FM, class R, int LM>
+__device__ void save_state(const KParams& K, int slot, int b, Tile<FM, R, LM>& T) {
   const size_t Bp = K.Bp;
   double* sd = K.state_d + (size_t)slot * state_doubles<FM>() * Bp + b;
-  Column<FM, R>& C = T.col;
+  Column<FM, R, LM>& C = T.col;
   for (int i = 0; i < C.n; i++) {
 #pragma unroll
     for (int k = 0; k < 5; k++) sd[(size_t)(k * FM + i) * Bp] = C.f(k, i);
@@ -490,11 +490,11 @@ __device__ void save_state(const KParams& K, int slot, int b, Tile<FM, R>& T) {
   uint8_t* sf = K.state_f + (size_t)slot * FM * Bp + b;
   for (int i = 0; i < C.n; i++) sf[(size_t)i * Bp] = C.gb[i * NT];
 }
-template <int FM, class R>
-__device__ void load_state(const KParams& K, int slot, int b, Tile<FM, R>& T) {
+template <int FM, class R, int LM>
+__device__ void load_state(const KParams& K, int slot, int b, Tile<FM, R, LM>& T) {
   const size_t Bp = K.Bp;
   const double* sd = K.state_d + (size_t)slot * state_doubles<FM>() * Bp + b;
-  Column<FM, R>& C = T.col;
+  Column<FM, R, LM>& C = T.col;
   const int32_t* si = K.state_i + (size_t)slot * NI_STATE * Bp + b;
   C.n = __ldcg(si);
   C.cntpk = (unsigned)__ldcg(si + Bp);
@@ -516,10 +516,10 @@ __device__ void load_state(const KParams& K, int slot, int b, Tile<FM, R>& T) {
 
 // load the column's parameters and derive the per-layer constants
 // (models/dpLGAR.py:41-57, data/utils.py:75-91 calc_m, GlobalParams.py:99-110)
-template <int FM, class R>
-__device__ void load_params(const KParams& K, int b, Tile<FM, R>& T) {
+template <int FM, class R, int LM>
+__device__ void load_params(const KParams& K, int b, Tile<FM, R, LM>& T) {
   const lgar_problem& p = K.p;
-  Column<FM, R>& C = T.col;
+  Column<FM, R, LM>& C = T.col;
   const size_t B = p.num_columns;
   C.L = p.num_layers;
   double cumv = 0.0;
@@ -578,7 +578,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // resident CTAs per SM are bounded by the shared-memory front lists: 1 (FM = 32, the fallback for the rare columns
 // that overflow 16 fronts), 2 (FM = 16), 3 (FM = 12), 4 (FM = 8); the register cap follows from that
-template <int FM, bool COUNT, bool DUMP>
+// LOGW: the instantiation launched with keep_checkpoints also logs the end points of the root finders (Column::logp);
+// in every other instantiation that code is compiled out
+template <int FM, bool COUNT, bool DUMP, bool LOGW = false>
 __global__ void __launch_bounds__(NT, (FM == 32) ? 1 : ((FM == 16) ? 2 : ((FM == 12) ? 3 : 4))) lgar_forward_kernel(const KParams K) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sm_fields = reinterpret_cast<double*>(smem_raw);                       // [5*FM][NT]
@@ -609,13 +611,13 @@ __global__ void __launch_bounds__(NT, (FM == 32) ? 1 : ((FM == 16) ? 2 : ((FM ==
   // resident (has passed this point) and SM resources free up, i.e. while this launch drains its last items
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  Tile<FM, double> T;
+  Tile<FM, double, LOGW ? 1 : 0> T;
   T.col.fb = sm_fields + threadIdx.x;
   T.col.ib = nullptr;
   T.col.gb = sm_flags + threadIdx.x;
   T.ctx.iter_cap = K.iter_cap;
   T.col.logp = nullptr;
-  T.col.log_pos = T.col.log_valid = T.col.log_mode = T.col.log_stride = 0;
+  T.col.log_pos = T.col.log_valid = T.col.log_stride = 0;
 
   for (;;) {
     if (lane == 0) {
@@ -686,11 +688,10 @@ __global__ void __launch_bounds__(NT, (FM == 32) ? 1 : ((FM == 16) ? 2 : ((FM ==
       load_state(K, slot_in, slot_cc, T);
     }
     precompute_psi_wp(T, p.wilting_point_psi);
-    if (K.slog && K.keep_ckpt) {  // log the end points of the root finders for the reverse pass
+    if (LOGW && K.slog && K.keep_ckpt) {  // log the end points of the root finders for the reverse pass
       T.col.logp = K.slog + (size_t)chunk * K.slog_cap * K.Bp + slot_cc;
       T.col.log_pos = 0;
       T.col.log_valid = valid ? K.slog_cap : 0;
-      T.col.log_mode = 1;
       T.col.log_stride = K.Bp;
     }
     const int site = (p.site_index && valid) ? __ldg(p.site_index + b) : 0;
@@ -753,7 +754,7 @@ __global__ void __launch_bounds__(NT, (FM == 32) ? 1 : ((FM == 16) ? 2 : ((FM ==
     // publish the state for the next chunk of this tile (release)
     const int slot_out = K.keep_ckpt ? chunk + 1 : 0;
     if (valid) save_state(K, slot_out, slot_c, T);
-    if (T.col.log_mode == 1 && valid) K.slog_count[(size_t)chunk * K.Bp + slot_c] = T.col.log_pos;
+    if (LOGW && K.slog && valid) K.slog_count[(size_t)chunk * K.Bp + slot_c] = T.col.log_pos;
     if (chunk == K.nchunks - 1 && valid) {
       if (K.o.sums) {
 #pragma unroll
