@@ -213,7 +213,7 @@ int lgar_backward(const lgar_problem* p, const double* grad_per_step, uint32_t g
  *                   Columns whose tape overflowed contribute 0 (see tape_overflow).
  *   tape_overflow   [B] or NULL: 1 where a column's tape arena was exhausted -- its gradient is not available
  *                   (per-column mode: NaN) and the caller must not step on it.
- *   partials        [ceil(B/32)][3 L] doubles of scratch for reduce != 0.
+ *   partials        [ceil(B/32)][3 LGAR_MAX_LAYERS + 1] doubles of scratch for reduce != 0.
  *   counters        [8] or NULL, diagnostics summed over warps: 0 cycles in the taped recompute, 1 cycles in the
  *                   reverse sweeps, 2 tape entries recorded (per lane), 3 sub-steps taped (per lane), 4 overflowed columns,
  *                   5-7 cycles of the taped recompute in the move sweep, in calc_dzdt (Geff), in the other Geff phases. */
@@ -228,6 +228,10 @@ typedef struct lgar_gradients {
   double* partials;
   int32_t* tape_overflow;
   unsigned long long* counters;
+  double* grad_ponded_depth_max; /* [B], or [1] with reduce; NULL = not wanted.  dL/d ponded_depth_max: the reference
+                                    declares it as a parameter in a commented-out line (models/dpLGAR.py:48-49); as a
+                                    leaf it reaches the loss through update_ponded_depth (models/dpLGAR.py:369-382) and
+                                    insert_water (Layer.py:1509-1532)                                              */
 } lgar_gradients;
 int lgar_backward_ex(const lgar_problem* p, const lgar_gradients* g, void* workspace_dev, size_t workspace_bytes,
                      void* stream);

@@ -54,7 +54,7 @@ class Gradients(C.Structure):
     _fields_ = [
         ("grad_per_step", _dp), ("grad_mask", C.c_uint32), ("reduce", C.c_int32), ("grad_sums", _dp),
         ("grad_alpha", _dp), ("grad_n", _dp), ("grad_ksat", _dp), ("partials", _dp), ("tape_overflow", _dp),
-        ("counters", _dp),
+        ("counters", _dp), ("grad_ponded_depth_max", _dp),
     ]
 
 

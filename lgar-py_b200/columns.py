@@ -94,7 +94,7 @@ class ColumnEnsemble:
     @property
     def num_steps(self): return self.forcing.shape[1]
 
-    def problem(self, alpha, n, ksat) -> _capi.Problem:
+    def problem(self, alpha, n, ksat, ponded_depth_max=None) -> _capi.Problem:
         p = _capi.Problem()
         p.abi_version = _capi.ABI_VERSION
         p.num_columns, p.num_layers, p.num_steps = self.num_columns, self.num_layers, self.num_steps
@@ -110,7 +110,8 @@ class ColumnEnsemble:
             p.giuh_ordinates[i] = float(g)
         p.alpha, p.n, p.ksat = alpha.data_ptr(), n.data_ptr(), ksat.data_ptr()
         p.theta_r, p.theta_e, p.thickness = self.theta_r.data_ptr(), self.theta_e.data_ptr(), self.thickness.data_ptr()
-        p.initial_psi, p.ponded_depth_max = self.initial_psi.data_ptr(), self.ponded_depth_max.data_ptr()
+        pdm = self.ponded_depth_max if ponded_depth_max is None else ponded_depth_max
+        p.initial_psi, p.ponded_depth_max = self.initial_psi.data_ptr(), pdm.data_ptr()
         p.forcing = self.forcing.data_ptr()
         p.site_index = self.site_index.data_ptr() if self.site_index is not None else None
         p.column_order = self.column_order.data_ptr() if self.column_order is not None else None
@@ -213,7 +214,7 @@ def _rerun_overflowed(ens: ColumnEnsemble, alpha, n, ksat, res: "ForwardResult",
 def forward_raw(ens: ColumnEnsemble, alpha, n, ksat, outputs=("runoff", "percolation"), per_step=True,
                 num_fronts=False, dump_fronts=False, counters=False, tile_cycles=False, keep_checkpoints=False,
                 workspace: Optional[torch.Tensor] = None, overflow_fallback=False, window=None,
-                into: Optional[ForwardResult] = None, pipeline_seq: int = 0) -> tuple[ForwardResult, torch.Tensor]:
+                into: Optional[ForwardResult] = None, pipeline_seq: int = 0, ponded_depth_max=None) -> tuple[ForwardResult, torch.Tensor]:
     """One persistent launch over all columns and all forcing steps (no autograd).
     overflow_fallback: rerun the columns that overflowed the front list with the 32-front kernel (synchronises:
     the status array is inspected on the host).
@@ -229,7 +230,9 @@ def forward_raw(ens: ColumnEnsemble, alpha, n, ksat, outputs=("runoff", "percola
     dev = ens.device
     alpha, n, ksat = _param(alpha, ens), _param(n, ens), _param(ksat, ens)
     B, T = ens.num_columns, ens.num_steps
-    p = ens.problem(alpha, n, ksat)
+    if ponded_depth_max is not None:  # [B] override of ens.ponded_depth_max (e.g. a learnable one)
+        ponded_depth_max = _dev_f64(ponded_depth_max, dev, (B,))
+    p = ens.problem(alpha, n, ksat, ponded_depth_max)
     if window is not None:
         p.step_begin, p.step_end = int(window[0]), int(window[1])
         if p.step_begin > 0:
@@ -277,7 +280,7 @@ def forward_raw(ens: ColumnEnsemble, alpha, n, ksat, outputs=("runoff", "percola
         rc = L_.lgar_forward(C.byref(p), C.byref(o), workspace.data_ptr(), workspace.numel(),
                              1 if keep_checkpoints else 0, C.c_void_p(stream))
     _capi.check(rc, "lgar_forward")
-    res._keep = (alpha, n, ksat, ens)  # keep inputs alive until the stream has consumed them
+    res._keep = (alpha, n, ksat, ens, ponded_depth_max)  # keep inputs alive until the stream has consumed them
     if overflow_fallback and not keep_checkpoints and not dump_fronts:
         res.overflow_reruns = _rerun_overflowed(ens, alpha, n, ksat, res, outputs, per_step)
     return res, workspace
@@ -289,13 +292,21 @@ class _LGARFunction(torch.autograd.Function):
     inside the library in a fixed order (no torch reduction kernel, bit-reproducible)."""
 
     @staticmethod
-    def forward(ctx, alpha, n, ksat, ens: ColumnEnsemble, mask: int):
+    def forward(ctx, alpha, n, ksat, pdm, ens: ColumnEnsemble, mask: int):
         outputs = [OUT_NAMES[k] for k in range(NUM_OUTPUTS) if (mask >> k) & 1]
-        need_grad = any(ctx.needs_input_grad[:3])
+        need_grad = any(ctx.needs_input_grad[:4])
+        B = ens.num_columns
+        pdm_b = None
+        if pdm is not None:
+            pdm_b = pdm.detach().to(ens.device, F64)
+            pdm_b = (pdm_b.reshape(1).expand(B) if pdm_b.numel() == 1 else pdm_b.reshape(B)).contiguous()
         res, ws = forward_raw(ens, alpha.detach(), n.detach(), ksat.detach(), outputs=outputs,
-                              keep_checkpoints=need_grad)
+                              keep_checkpoints=need_grad, ponded_depth_max=pdm_b)
         ctx.ens, ctx.mask, ctx.ws = ens, mask, ws
         ctx.save_for_backward(*res._keep[:3])
+        ctx.pdm_b = res._keep[4]
+        ctx.pdm_shape = None if pdm is None else tuple(pdm.shape)
+        ctx.want_pdm = pdm is not None and ctx.needs_input_grad[3]
         ctx.in_shapes = (alpha.shape, n.shape, ksat.shape)
         ctx.mark_non_differentiable(res.status, res.crash_step, res.start_volume)
         per_step = res.per_step if res.per_step is not None else torch.zeros(0, dtype=F64, device=ens.device)
@@ -308,14 +319,19 @@ class _LGARFunction(torch.autograd.Function):
         alpha, n, ksat = ctx.saved_tensors
         dev = ens.device
         Lr, B = ens.num_layers, ens.num_columns
-        p = ens.problem(alpha, n, ksat)
+        p = ens.problem(alpha, n, ksat, ctx.pdm_b)
         sa, sn, sk = ctx.in_shapes
-        shared = len(sa) == 1 and len(sn) == 1 and len(sk) == 1
+        pdm_shared = ctx.pdm_shape is None or int(torch.Size(ctx.pdm_shape).numel()) == 1
+        shared = len(sa) == 1 and len(sn) == 1 and len(sk) == 1 and (pdm_shared or not ctx.want_pdm)
         g = _capi.Gradients()
         gshape = (Lr,) if shared else (Lr, B)
         ga = torch.zeros(gshape, dtype=F64, device=dev)
         gn = torch.zeros_like(ga)
         gk = torch.zeros_like(ga)
+        gp = None
+        if ctx.want_pdm:
+            gp = torch.zeros(1 if shared else B, dtype=F64, device=dev)
+            g.grad_ponded_depth_max = gp.data_ptr()
         gps = g_per_step.contiguous() if (g_per_step is not None and g_per_step.numel()) else None
         gs = g_sums.contiguous() if g_sums is not None else None
         overflow = torch.empty(B, dtype=torch.int32, device=dev)
@@ -326,7 +342,7 @@ class _LGARFunction(torch.autograd.Function):
         g.tape_overflow = overflow.data_ptr()
         partials = None
         if shared:
-            partials = torch.empty(((B + 31) // 32, 3 * _capi.MAX_LAYERS), dtype=F64, device=dev)
+            partials = torch.empty(((B + 31) // 32, 3 * _capi.MAX_LAYERS + 1), dtype=F64, device=dev)
             g.reduce, g.partials = 1, partials.data_ptr()
         counters = None
         if ens.reverse_counters:
@@ -343,11 +359,16 @@ class _LGARFunction(torch.autograd.Function):
 
         def shape_back(gr, shp):
             return gr.sum(dim=1) if (len(shp) == 1 and gr.dim() == 2) else gr
-        return shape_back(ga, sa), shape_back(gn, sn), shape_back(gk, sk), None, None
+        gp_out = None
+        if gp is not None:
+            gp_out = (gp.sum() if (pdm_shared and gp.numel() > 1) else gp).reshape(ctx.pdm_shape)
+        return shape_back(ga, sa), shape_back(gn, sn), shape_back(gk, sk), gp_out, None, None
 
 
-def lgar_columns(alpha, n, ksat, ens: ColumnEnsemble, outputs=("runoff", "percolation")):
+def lgar_columns(alpha, n, ksat, ens: ColumnEnsemble, outputs=("runoff", "percolation"), ponded_depth_max=None):
     """Differentiable batched run.  alpha/n/ksat: `[L,B]` (per column) or `[L]` (shared by all columns).
+    ponded_depth_max (optional): a scalar (shared) or `[B]` tensor that replaces ens.ponded_depth_max; if it requires
+    grad it is a gradient leaf like alpha/n/ksat (the reference's commented-out parameter, models/dpLGAR.py:48-49).
     Returns a dict: every requested output as `[T,B]`, plus `sums[NOUT,B]`, `start_volume[B]`,
     `status[B]`, `crash_step[B]`."""
     mask = output_mask(outputs)
@@ -359,7 +380,8 @@ def lgar_columns(alpha, n, ksat, ens: ColumnEnsemble, outputs=("runoff", "percol
         a = a if a.dim() == 2 else a.unsqueeze(1).expand(ens.num_layers, ens.num_columns)
         nn_ = nn_ if nn_.dim() == 2 else nn_.unsqueeze(1).expand(ens.num_layers, ens.num_columns)
         k = k if k.dim() == 2 else k.unsqueeze(1).expand(ens.num_layers, ens.num_columns)
-    per_step, sums, sv, st, cs = _LGARFunction.apply(a.contiguous(), nn_.contiguous(), k.contiguous(), ens, mask)
+    pdm = None if ponded_depth_max is None else torch.as_tensor(ponded_depth_max, dtype=F64).to(dev)
+    per_step, sums, sv, st, cs = _LGARFunction.apply(a.contiguous(), nn_.contiguous(), k.contiguous(), pdm, ens, mask)
     out = {name: per_step[bin(mask & ((1 << OUT_NAMES.index(name)) - 1)).count("1")] for name in outputs}
     out.update(sums=sums, start_volume=sv, status=st, crash_step=cs)
     return out

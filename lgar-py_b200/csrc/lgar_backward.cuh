@@ -30,7 +30,8 @@
 
 namespace lgar {
 
-constexpr int NPAR_IDS = 3 * MAXL;  // alpha[l] = 3l, n[l] = 3l+1, ksat[l] = 3l+2
+constexpr int NPAR_IDS = 3 * MAXL + 1;  // alpha[l] = 3l, n[l] = 3l+1, ksat[l] = 3l+2; ponded_depth_max = 3 MAXL
+constexpr int ID_PDM = 3 * MAXL;
 template <int FM>
 __host__ __device__ constexpr int leaf_fields() { return NPAR_IDS; }                  // + fld*FM + i
 template <int FM>
@@ -62,6 +63,7 @@ struct BParams {
   double* grad_alpha;           // [L][B]
   double* grad_n;
   double* grad_ksat;
+  double* grad_pdm;             // [B] (or [1] with reduce) dL/d ponded_depth_max, or NULL
   // per resident warp scratch
   TapeEntry* tape;              // [slots][arena_cap][32]: the tapes of all sub-steps of one chunk, back to back
   unsigned char* meta;          // [slots][ring_steps][32] StepMeta
@@ -83,7 +85,7 @@ struct BParams {
 // second stage of the shared-parameter reduction: block q sums partials[.][q] over the tiles in a fixed order
 // (lane j takes tiles j, j+32, ... sequentially, then a butterfly over the 32 lane sums)
 __global__ void lgar_reduce_tile_partials(const double* partials, int ntiles, int L, double* grad_alpha, double* grad_n,
-                                          double* grad_ksat) {
+                                          double* grad_ksat, double* grad_pdm) {
   const int q = blockIdx.x;  // 3 l + {0: alpha, 1: n, 2: ksat}
   double s = 0.0;
   for (int t = threadIdx.x; t < ntiles; t += 32) s += partials[(size_t)t * NPAR_IDS + q];
@@ -91,7 +93,9 @@ __global__ void lgar_reduce_tile_partials(const double* partials, int ntiles, in
   for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
   if (threadIdx.x == 0) {
     const int l = q / 3;
-    if (l < L) {
+    if (q == ID_PDM) {
+      if (grad_pdm) grad_pdm[0] = s;
+    } else if (l < L) {
       double* out = (q % 3 == 0) ? grad_alpha : ((q % 3 == 1) ? grad_n : grad_ksat);
       out[l] = s;
     }
@@ -185,6 +189,7 @@ __global__ void __launch_bounds__(NT, 2) lgar_backward_kernel(const BParams P) {
       C.soil[l].id_ksat = 3 * l + 2;
       C.soil[l].id_m = -1;
     }
+    C.id_pdm = P.grad_pdm ? ID_PDM : -1;  // ponded_depth_max as a gradient leaf (models/dpLGAR.py:48, commented out upstream)
     const int site = (p.site_index && valid) ? __ldg(p.site_index + b) : 0;
     const double* frc = p.forcing + (size_t)site * Tn * 2;
     double gpar[NPAR_IDS];
@@ -392,6 +397,7 @@ __global__ void __launch_bounds__(NT, 2) lgar_backward_kernel(const BParams P) {
         P.grad_n[(size_t)l * B + b] = overflow ? qnan : gpar[3 * l + 1];
         P.grad_ksat[(size_t)l * B + b] = overflow ? qnan : gpar[3 * l + 2];
       }
+      if (P.grad_pdm) P.grad_pdm[b] = overflow ? qnan : gpar[ID_PDM];
     }
     if (chunk == 0 && valid && P.tape_overflow) P.tape_overflow[b] = overflow ? 1 : 0;
     if (P.counters) {

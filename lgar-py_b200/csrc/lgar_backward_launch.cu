@@ -59,7 +59,7 @@ static int launch_backward(BParams& P, int S, int chunk, int slots, int arena_ca
   BW_TRY(cudaGetLastError());
   if (P.reduce) {
     lgar_reduce_tile_partials<<<NPAR_IDS, 32, 0, st>>>(P.partials, P.K.ntiles, P.K.p.num_layers, P.grad_alpha, P.grad_n,
-                                                      P.grad_ksat);
+                                                      P.grad_ksat, P.grad_pdm);
     BW_TRY(cudaGetLastError());
   }
   return 0;

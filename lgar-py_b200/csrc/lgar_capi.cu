@@ -386,6 +386,7 @@ int lgar_backward_ex(const lgar_problem* p, const lgar_gradients* g, void* works
   P.grad_alpha = g->grad_alpha;
   P.grad_n = g->grad_n;
   P.grad_ksat = g->grad_ksat;
+  P.grad_pdm = g->grad_ponded_depth_max;
   P.tape_overflow = g->tape_overflow;
   P.reduce = g->reduce ? 1 : 0;
   P.partials = g->partials;

@@ -1508,6 +1508,11 @@ struct Column {
   double cum[MAXL];  // cumulative layer thickness (GlobalParams.py:103-110)
   double thick[MAXL];
   double pdm;        // ponded_depth_max
+  int id_pdm;        // TAPED: tape id of ponded_depth_max when its gradient is requested (dpLGAR.py:48), else -1
+  __device__ __forceinline__ R pdmR() const {
+    if constexpr (TAPED) return Var(pdm, id_pdm);
+    else return pdm;
+  }
   R psi_wp;          // AET: capillary head at which AET = 0.5 PET (aet.py:37-43); column constant
   R ponded_water, ending_volume;
   double previous_precip;

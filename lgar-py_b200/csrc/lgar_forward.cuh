@@ -207,16 +207,16 @@ __device__ void substep(Tile<FM, R, LM>& T, bool act, double precip_rate, double
           infiltration_sub = tmin(ponded_depth_sub, fp_cm);
           ponded_depth_sub = ponded_depth_sub - infiltration_sub;
         } else if (ponded_temp > C.pdm) {
-          ponded_depth_sub = R(C.pdm);
+          ponded_depth_sub = C.pdmR();
           infiltration_sub = fp_cm;
         } else {
           c.br[1]++;  // equality: neither branch of the reference runs (Q8)
         }
-        runoff_sub = clamp_min_(ponded_temp - C.pdm, 0.0);
+        runoff_sub = clamp_min_(ponded_temp - C.pdmR(), 0.0);
       } else {
         infiltration_sub = tmin(ponded_depth_sub, fp_cm);
         const R r_ = ponded_depth_sub - infiltration_sub;
-        ponded_depth_sub = R(C.pdm);
+        ponded_depth_sub = C.pdmR();
         runoff_sub = clamp_min_(r_, 0.0);
       }
       T.acc[LGAR_OUT_INFILTRATION] = T.acc[LGAR_OUT_INFILTRATION] + infiltration_sub;
@@ -292,8 +292,8 @@ __device__ void substep(Tile<FM, R, LM>& T, bool act, double precip_rate, double
       ponded_water_sub = ponded_depth_sub;
       ponded_depth_sub = R(0.0);
     } else {
-      runoff_sub = ponded_depth_sub - C.pdm;
-      ponded_depth_sub = R(C.pdm);
+      runoff_sub = ponded_depth_sub - C.pdmR();
+      ponded_depth_sub = C.pdmR();
       ponded_water_sub = ponded_depth_sub;
     }
     T.acc[LGAR_OUT_RUNOFF] = T.acc[LGAR_OUT_RUNOFF] + runoff_sub;
@@ -540,6 +540,7 @@ __device__ void load_params(const KParams& K, int b, Tile<FM, R, LM>& T) {
     C.cum[l] = cumv;
   }
   C.pdm = __ldg(p.ponded_depth_max + b);
+  C.id_pdm = -1;
 }
 
 // ------------------------------------------------------------------------------------

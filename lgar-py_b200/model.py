@@ -160,7 +160,10 @@ class dpLGAR(nn.Module):
         a, n, k = self._params()
         ens = self._ensemble(torch.as_tensor(x, dtype=torch.float64))
         self.last_ensemble = ens  # (the reverse pass leaves its tape-overflow flags there)
-        out = lgar_columns(a, n, k, ens, outputs=outputs)
+        # ponded_depth_max as a learnable parameter (models/dpLGAR.py:48, commented out upstream): make it one with
+        # `model.ponded_depth_max = nn.Parameter(model.ponded_depth_max)` and it receives a gradient like alpha/n/ksat
+        pdm = self.ponded_depth_max if getattr(self.ponded_depth_max, "requires_grad", False) else None
+        out = lgar_columns(a, n, k, ens, outputs=outputs, ponded_depth_max=pdm)
         if on_status != "ignore":
             st = out["status"]
             if bool((st != 0).any()):

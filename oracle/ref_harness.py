@@ -146,12 +146,17 @@ def run_reference(
     record_fronts=True,
     grad_losses=None,             # e.g. ("AET","infiltration","runoff","final_volume")
     verbose=False,
+    pdm_leaf=False,               # ponded_depth_max as nn.Parameter: what the commented-out line dpLGAR.py:48 does
 ):
     """Returns dict of numpy arrays.  Per-step outputs are the model accumulators read
     after each forward() and then zeroed (== MassBalance.change_mass semantics)."""
     torch, _, dpLGAR = _import_reference()
     cfg = build_cfg(**(cfg_kwargs or {}))
     model = dpLGAR(cfg)
+    if pdm_leaf:  # set on the instance (the reference source is not touched); set_internal_states() hands a clone of
+        # it to GlobalParams (dpLGAR.py:104, GlobalParams.py:22), so autograd reaches it through every use
+        model.ponded_depth_max = torch.nn.Parameter(model.ponded_depth_max.detach().clone())
+        model.set_internal_states()
     if alpha is not None or n is not None or ksat is not None:
         with torch.no_grad():
             for i in range(len(model.alpha)):
@@ -225,6 +230,10 @@ def run_reference(
                     [0.0 if gi is None else float(gi) for gi in g]
                 ).reshape(3, L)  # rows: alpha, n, ksat
                 out[f"loss_{lname}"] = float(loss)
+                if pdm_leaf:
+                    gp = torch.autograd.grad(loss, [model.ponded_depth_max], retain_graph=True, allow_unused=True)[0] \
+                        if getattr(loss, "requires_grad", False) else None
+                    out[f"grad_{lname}_pdm"] = 0.0 if gp is None else float(gp)
     return out
 
 

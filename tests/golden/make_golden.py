@@ -115,6 +115,9 @@ def cases():
     c["frozen_ens_col8074"] = dict(ens=(8074, 160), cfg=dict(**FF))      # free-drainage front in layer 2 (Q18) with the factor
     c["frozen_rand_phil_0"] = dict(forcing=(PHIL, 4500, 400), cfg=dict(**FF), alpha=al[8], n=nn[8], ksat=ks[8])
     c["grad_frozen_phil_4550_150"] = dict(forcing=(PHIL, 4550, 150), grad=G, cfg=dict(**FF))
+    # ponded_depth_max as a gradient leaf (models/dpLGAR.py:48-49): 0.2 cm binds in this window (ponding
+    # reaches 0.4 cm), so runoff and the later infiltration depend on it
+    c["grad_pdmleaf_phil_4550_150"] = dict(forcing=(PHIL, 4550, 150), grad=G, cfg=dict(ponded_depth_max=0.2), pdm_leaf=True)
     # full-year known answers (config[0]); no per-step front dump to keep the files small
     c["phil_year"] = dict(forcing=(PHIL, 0, 8760), fronts=False)
     c["bush_year"] = dict(forcing=(BUSH, 0, 8760), cfg=dict(layer_soil_type=(15, 16, 17)),
@@ -144,7 +147,7 @@ def run_case(name):
     r = run_reference(
         f, cfg_kwargs=spec.get("cfg"), alpha=spec.get("alpha"), n=spec.get("n"),
         ksat=spec.get("ksat"), record_fronts=spec.get("fronts", True),
-        grad_losses=spec.get("grad"))
+        grad_losses=spec.get("grad"), pdm_leaf=bool(spec.get("pdm_leaf", False)))
     cfg = dict(layer_thickness=(44.0, 131.0, 25.0), ponded_depth_max=0.0, subcycle_length=3600.0,
                forcing_resolution=3600.0, initial_psi=2000.0, wilting_point_psi=15495.0,
                nint=120, frozen_factor=1.0, giuh_ordinates=(0.06, 0.51, 0.28, 0.12, 0.03), use_closed_form_G=False)

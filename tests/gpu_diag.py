@@ -7,7 +7,7 @@ import lgar_b200
 from lgar_b200 import workloads, ColumnEnsemble, forward_raw
 shapes = [tuple(int(x) for x in a.split("x")) for a in sys.argv[1:]] or [(2048, 256)]
 for B, T in shapes:
-    we = workloads.synthetic_sites_ensemble(B=B, T=T, sites=max(1, min(128, B // 32)), rank=0)
+    we = workloads.synthetic_sites_ensemble(B=B, T=T, sites=max(1, min(128, B // 32)), rank=int(os.environ.get("LGAR_DIAG_RANK", "0")))
     sl = os.environ.get("LGAR_DIAG_SLICE")
     if sl:
         a, cnt = (int(x) for x in sl.split(":"))
