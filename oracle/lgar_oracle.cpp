@@ -30,6 +30,9 @@
 #include <thread>
 #include <type_traits>
 #include <vector>
+#ifdef LGAR_ORACLE_DEVICE_POW
+#include "../lgar-py_b200/csrc/lgar_pow.cuh"
+#endif
 
 #define LGAR_LMAX 8
 #define LGAR_FMAX 16
@@ -143,9 +146,22 @@ static inline Dual operator/(double a, const Dual& b) { return Dual(a) / b; }
 
 // torch.pow(base, exponent) with torch's backward conventions
 // (pow_backward_self: 0 where exponent==0 ; pow_backward_exponent: 0 where base==0 && exponent>=0)
+#ifdef LGAR_ORACLE_DEVICE_POW
+// Second build of the oracle (liblgar_oracle_devpow.so, tests only): pow through the CUDA path's own table-driven
+// routine (lgar-py_b200/csrc/lgar_pow.cuh compiles for the host with the same operations) instead of glibc's.  The two
+// pows differ in the last bit in ~0.035 % of calls; LGAR's discrete decisions (front creation, merging, root-finder
+// exits) can amplify one such bit into a different trajectory for an ill-conditioned column.  With this build the
+// oracle and the CUDA kernels execute the same arithmetic, so every remaining difference would be a logic defect.
+static inline double pow_(double a, double b) {
+  if (b == 2.0) return a * a;  // the CUDA closures square by multiplication (== glibc's pow(x, 2.0) bit for bit)
+  double r;
+  return lgar::pow_fast(a, b, &r) ? r : std::pow(a, b);
+}
+#else
 static inline double pow_(double a, double b) { return std::pow(a, b); }
+#endif
 static inline Dual pow_(const Dual& a, const Dual& b) {
-  Dual r; r.v = std::pow(a.v, b.v);
+  Dual r; r.v = pow_(a.v, b.v);
   double da = (b.v == 0.0) ? 0.0 : b.v * std::pow(a.v, b.v - 1.0);
   double db = (a.v == 0.0 && b.v >= 0.0) ? 0.0 : r.v * std::log(a.v);
   for (int i = 0; i < LGAR_NT; i++) {
@@ -172,9 +188,16 @@ static inline Dual abs_(const Dual& a) {
   for (int i = 0; i < LGAR_NT; i++) r.d[i] = a.d[i] * s;
   return r;
 }
-static inline double min_(double a, double b) { return (b < a) ? b : a; }  // NaN-free domain
+// torch.min / torch.minimum (binary) PROPAGATE NaN (unlike fmin): calc_dry_depth hands torch.min a NaN when the top
+// front sits at theta_e exactly (Layer.py:1318-1333: delta_theta = 0, tau = inf, geff = 0, tau * geff = NaN) -- golden
+// nan_dry_depth_col185
+static inline double min_(double a, double b) {
+  if (std::isnan(a) || std::isnan(b)) return a + b;
+  return (b < a) ? b : a;
+}
 static inline Dual min_(const Dual& a, const Dual& b) {
-  // torch.min / torch.minimum (binary): gradient split 0.5/0.5 at ties (Q13)
+  // gradient split 0.5/0.5 at ties (Q13)
+  if (std::isnan(a.v) || std::isnan(b.v)) return Dual(a.v + b.v);
   if (a.v < b.v) return a;
   if (b.v < a.v) return b;
   Dual r; r.v = a.v;

@@ -36,25 +36,48 @@ class OracleCfg(C.Structure):
 
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "lgar_oracle.cpp")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    dev = os.path.join(_HERE, "liblgar_oracle_devpow.so")
+    if (force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src)
+            or not os.path.exists(dev) or os.path.getmtime(dev) < os.path.getmtime(src)):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
 
 
-_lib = None
+_libs = {}
+_variant = "glibc"
+
+
+class device_pow:
+    """Context manager: inside it every oracle call runs liblgar_oracle_devpow.so, the same restatement with the CUDA
+    path's table-driven pow (lgar-py_b200/csrc/lgar_pow.cuh, compiled for the host) instead of glibc's.  Purpose: the two
+    pows differ in the last bit in ~0.035 % of calls, which an ill-conditioned column can amplify into another
+    trajectory; with the same pow on both sides any remaining difference is a logic defect of the CUDA path."""
+
+    def __enter__(self):
+        global _variant
+        self._old, _variant = _variant, "devpow"
+        return self
+
+    def __exit__(self, *exc):
+        global _variant
+        _variant = self._old
+        return False
 
 
 def lib():
-    global _lib
-    if _lib is None:
+    if _variant not in _libs:
         build()
-        _lib = C.CDLL(_SO)
-        assert _lib.lgar_oracle_sizeof_cfg() == C.sizeof(OracleCfg)
-        _lib.lgar_oracle_forward.restype = C.c_int
-        _lib.lgar_oracle_forward_tangent.restype = C.c_int
-        _lib.lgar_oracle_forward_batch.restype = C.c_int
-        _lib.lgar_oracle_forward_batch_ex.restype = C.c_int
-    return _lib
+        so = _SO if _variant == "glibc" else os.path.join(_HERE, "liblgar_oracle_devpow.so")
+        if not os.path.exists(so):
+            subprocess.check_call(["make", "-C", _HERE, "-s"])
+        l = C.CDLL(so)
+        assert l.lgar_oracle_sizeof_cfg() == C.sizeof(OracleCfg)
+        l.lgar_oracle_forward.restype = C.c_int
+        l.lgar_oracle_forward_tangent.restype = C.c_int
+        l.lgar_oracle_forward_batch.restype = C.c_int
+        l.lgar_oracle_forward_batch_ex.restype = C.c_int
+        _libs[_variant] = l
+    return _libs[_variant]
 
 
 def make_cfg(alpha, n, ksat, theta_r, theta_e, thickness=(44.0, 131.0, 25.0), dt_h=1.0,

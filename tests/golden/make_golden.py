@@ -118,6 +118,11 @@ def cases():
     # ponded_depth_max as a gradient leaf (models/dpLGAR.py:48-49): 0.2 cm binds in this window (ponding
     # reaches 0.4 cm), so runoff and the later infiltration depend on it
     c["grad_pdmleaf_phil_4550_150"] = dict(forcing=(PHIL, 4550, 150), grad=G, cfg=dict(ponded_depth_max=0.2), pdm_leaf=True)
+    # torch.min propagates NaN: column 185 of the C4 bench shard (a column whose top front has already been pushed to a
+    # negative depth) reaches calc_dry_depth with theta == theta_e exactly: delta_theta = 0, tau = inf, Geff = 0,
+    # tau * geff = NaN, and torch.min(cum_thickness, NaN) = NaN (Layer.py:1331-1333); the run dies one step later in
+    # error_check.  Found by bench.py's parity block (the oracle's min_ used to drop the NaN).
+    c["nan_dry_depth_col185"] = dict(ens_big=(185, 5160), fronts=False)
     # full-year known answers (config[0]); no per-step front dump to keep the files small
     c["phil_year"] = dict(forcing=(PHIL, 0, 8760), fronts=False)
     c["bush_year"] = dict(forcing=(BUSH, 0, 8760), cfg=dict(layer_soil_type=(15, 16, 17)),
@@ -129,16 +134,19 @@ def run_case(name):
     from oracle.ref_harness import read_forcing_cm_per_h, run_reference
 
     spec = cases()[name]
-    if "ens" in spec:
+    if "ens" in spec or "ens_big" in spec:
         import lgar_b200  # noqa: F401  (numpy-only workload generator; no GPU needed)
         from lgar_b200 import workloads
-        col, T_ = spec["ens"]
-        we = workloads.synthetic_sites_ensemble(B=16000, T=2560, sites=128, rank=0)
+        big = "ens_big" in spec
+        col, T_ = spec["ens_big" if big else "ens"]
+        we = (workloads.synthetic_sites_ensemble(B=125_000, T=8760, sites=128, rank=0) if big  # the C4 bench shard
+              else workloads.synthetic_sites_ensemble(B=16000, T=2560, sites=128, rank=0))
         site = int(we.site_index[col])
         f = we.forcing[site, :T_].copy()
         spec = dict(spec, alpha=we.alpha[:, col], n=we.n[:, col], ksat=we.ksat[:, col],
                     cfg=dict(spec.get("cfg") or {}, layer_soil_type=(12, 13, 14) if site % 2 == 0 else (15, 16, 17)))
-        path, start, count = f"workloads.synthetic_sites_ensemble(B=16000,T=2560,sites=128,rank=0)/site{site}/col{col}", 0, T_
+        path, start, count = (f"workloads.synthetic_sites_ensemble(B={'125000,T=8760' if big else '16000,T=2560'},sites=128,rank=0)"
+                              f"/site{site}/col{col}"), 0, T_
     else:
         path, start, count = spec["forcing"]
         f = read_forcing_cm_per_h(path)
