@@ -70,6 +70,10 @@ def parse():
     ap.add_argument("--no-pyref", action="store_true", help="reference arm: skip the Python reference (port only)")
     ap.add_argument("--pyref-rows", type=int, default=0, help="reference arm: forcing rows per step of the Python reference")
     ap.add_argument("--pyref-procs", type=int, default=0, help="reference arm: processes of the Python reference (default min(8, cores))")
+    ap.add_argument("--shard-rank", type=int, default=-1,
+                    help="diagnosis: run the shard of this rank of a multi-GPU job on a single GPU (shard vs GPU differences)")
+    ap.add_argument("--rank-sites", action="store_true",
+                    help="A/B: every rank draws its own site records too (shards then differ in work by several per cent)")
     ap.add_argument("--grad-columns", type=int, default=-1,
                     help="columns of the shard used for the forward+gradient figure (-1 = the whole shard, 0 = skip)")
     args = ap.parse_args()
@@ -90,14 +94,17 @@ def workload_name(args):
         return (f"C3: Bushland resampled forcing, {args.columns}-member parameter ensemble per GPU x {args.nsteps} hourly "
                 "steps, 3 layers, forward only, alpha~U[0.0015,0.015] n~U[1.1,3] Ks~logU[0.01,30]")
     return (f"C4 shard per GPU: {args.columns} columns x {args.nsteps} hourly steps, 3 layers, {args.sites} synthetic "
-            "sites, alpha~U[0.0015,0.015] n~U[1.1,3] Ks~logU[0.01,30]")
+            "sites, alpha~U[0.0015,0.015] n~U[1.1,3] Ks~logU[0.01,30]"
+            + (" (every rank: own site records)" if args.rank_sites else "")
+            + (f" (shard of rank {args.shard_rank})" if args.shard_rank >= 0 else ""))
 
 
 def make_workload(args, rank):
     from lgar_b200 import workloads
     if args.workload == "c3":
         return workloads.bushland_ensemble(B=args.columns, T=args.nsteps, seed=rank)
-    return workloads.synthetic_sites_ensemble(B=args.columns, T=args.nsteps, sites=args.sites, rank=rank)
+    return workloads.synthetic_sites_ensemble(B=args.columns, T=args.nsteps, sites=args.sites, rank=rank,
+                                              shared_sites=not args.rank_sites)
 
 
 def segments(T, steps):
@@ -350,7 +357,7 @@ def main():
     _capi.check(_capi.lib().lgar_device_check(), "lgar_device_check")
 
     B, T = args.columns, args.nsteps
-    we = make_workload(args, rank)
+    we = make_workload(args, rank if args.shard_rank < 0 else args.shard_rank)
     S = we.forcing.shape[0]
     segs = segments(T, args.steps)
     nseg = len(segs)
@@ -571,7 +578,7 @@ def main():
     # per-rank pass time, SM clock, power (diagnosis of weak-scaling losses: which rank / GPU was the slow one)
     my_clk = sampler.summary()
     per_rank = torch.tensor([total_ms, float(my_clk["sm_mhz"] or 0.0), float(my_clk["power_w"] or 0.0),
-                             1.0 if my_clk["reasons"] else 0.0, float(alive_steps), fg[0] if fg else 0.0],
+                             1.0 if my_clk["reasons"] else 0.0, float(alive_steps), fg[0] if fg else 0.0, flop_per_pass],
                             dtype=torch.float64, device=dev)
     if world > 1:
         gathered = [torch.zeros_like(per_rank) for _ in range(world)]
@@ -622,7 +629,10 @@ def main():
         "clocks": my_clk,
         "per_rank": {"pass_ms": [float(g[0]) for g in gathered], "sm_mhz": [float(g[1]) for g in gathered],
                      "power_w": [float(g[2]) for g in gathered], "throttle_reason_seen": [bool(g[3] > 0) for g in gathered],
-                     "alive_column_steps": [float(g[4]) for g in gathered], "fwd_grad_ms": [float(g[5]) for g in gathered]},
+                     "alive_column_steps": [float(g[4]) for g in gathered], "fwd_grad_ms": [float(g[5]) for g in gathered],
+                     # algorithmic flop of each rank's shard (its own counting pass) / its own pass time: equal rates with
+                     # unequal pass times = the shards differ in work, not the GPUs in speed
+                     "achieved_tflops": [float(g[6]) / (float(g[0]) * 1e-3) / 1e12 for g in gathered]},
         "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak if fp64_peak else None, "traffic": traffic, "traffic_source": traffic_note,
                      "peak_source": "in-run DFMA probe (lgar_measure_fp64_flops); MEASURED_PEAKS.json has no FP64 entry",

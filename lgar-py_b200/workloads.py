@@ -65,12 +65,19 @@ def bushland_ensemble(B: int = 100_000, T: int = 8760, seed: int = 0) -> Ensembl
 
 
 def synthetic_sites_ensemble(B: int = 125_000, T: int = 8760, sites: int = 128, seed: int = 1,
-                             forcing_seed: int = 1234, rank: int = 0) -> Ensemble:
+                             forcing_seed: int = 1234, rank: int = 0, shared_sites: bool = False) -> Ensemble:
     """C4 shard for one GPU: `sites` synthetic site records (Phillipsburg / Bushland alternating,
     24 h-block log-normal storm scaling sigma = 0.3, circular shift by whole days), each shared by
-    ~B/sites parameter members.  Rank r of an N-GPU job draws shard r of the 1M-column ensemble."""
+    ~B/sites parameter members.  Rank r of an N-GPU job draws shard r of the 1M-column ensemble.
+
+    shared_sites=False: every rank also draws its own `sites` records (N x sites sites in the job).
+    shared_sites=True (bench.py): the job has `sites` sites in total and rank r holds ITS members of every
+    site (own parameter draws, the site records of rank 0), so the shards are statistically equivalent --
+    the weak-scaling shape.  With rank-specific records the pass times of two shards differed by 9 % at equal
+    clocks and column-steps (profiles/bench_r2_n2_rank_sites.json: 19.6 s and 21.4 s), which reads as a
+    scaling loss although no GPU waits for another.  Rank 0's shard is the same either way."""
     rng = np.random.default_rng([seed, rank])
-    frng = np.random.default_rng([forcing_seed, rank])
+    frng = np.random.default_rng([forcing_seed, 0 if shared_sites else rank])
     a, n, k = sample_parameters(rng, B)
     base = {s: base_forcing(s) for s in ("phil", "bush")}
     full_T = base["phil"].shape[0]
