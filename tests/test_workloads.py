@@ -21,6 +21,21 @@ def test_c4_shard_shapes_and_determinism():
     assert (a.forcing >= 0).all()
 
 
+def test_shared_site_records_give_equivalent_shards():
+    """bench.py's weak-scaling shape: every rank holds its own members of the SAME site records; rank 0's shard does not
+    depend on the switch (the single-GPU bench lines of all rounds stay comparable)."""
+    r0 = workloads.synthetic_sites_ensemble(B=640, T=120, sites=4, rank=0)
+    s0 = workloads.synthetic_sites_ensemble(B=640, T=120, sites=4, rank=0, shared_sites=True)
+    s3 = workloads.synthetic_sites_ensemble(B=640, T=120, sites=4, rank=3, shared_sites=True)
+    r3 = workloads.synthetic_sites_ensemble(B=640, T=120, sites=4, rank=3)
+    for k in ("alpha", "n", "ksat", "forcing", "theta_r", "theta_e", "site_index"):
+        np.testing.assert_array_equal(getattr(r0, k), getattr(s0, k))
+    np.testing.assert_array_equal(s3.forcing, s0.forcing)       # same sites ...
+    np.testing.assert_array_equal(s3.alpha, r3.alpha)           # ... the rank's own parameter members
+    assert not np.array_equal(s3.alpha, s0.alpha)
+    assert not np.array_equal(r3.forcing, r0.forcing)           # (the A/B variant: own site records per rank)
+
+
 def test_c3_bushland_ensemble():
     e = workloads.bushland_ensemble(B=64, T=100)
     assert e.forcing.shape == (1, 100, 2) and (e.site_index == 0).all()
