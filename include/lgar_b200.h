@@ -152,7 +152,7 @@ typedef struct lgar_outputs {
   double* per_step;        /* [popcount(per_step_mask)][T][B]: the selected outputs, compact, in
                               increasing output index                                            */
   uint32_t per_step_mask;  /* bit k = store output k                                            */
-  int32_t reserved0;
+  int32_t tile_diag_rows;  /* rows of `tile_cycles` (0 = 1); see there                             */
   double* sums;            /* [NOUT][B]: sum over t of every output (ENDING_VOLUME and
                               PONDED_WATER: value after the last step)                          */
   double* start_volume;    /* [B] water in the column after set_internal_states()               */
@@ -171,8 +171,11 @@ typedef struct lgar_outputs {
                                    dry-over-wet fixes (Layer.py:1055-1096), insert_water equality fall-through
                                    (Layer.py:1509-1521), calc_bottom_sum_f_p with the free-drainage front in
                                    layer >= 2 (Layer.py:1538-1555)                                          */
-  /* diagnostics: SM cycles spent on each tile of 32 consecutive columns, summed over chunks     */
-  unsigned long long* tile_cycles; /* [ceil(B/32)]                                              */
+  /* diagnostics: SM cycles spent on each tile of 32 consecutive columns, summed over chunks.  With
+   * tile_diag_rows = 3 (and `counters` set: the counting kernel) two more rows follow: cycles the tile's chunks
+   * spent WAITING for their predecessor chunk (a resident warp blocked on the per-tile progress counter), and the
+   * global timer (ns) at the end of the tile's last chunk of this launch -- the scheduler's idle time and tail */
+  unsigned long long* tile_cycles; /* [tile_diag_rows][ceil(B/32)]                              */
 } lgar_outputs;
 
 /* Library / device probe.  Returns 0 if an sm_100 device is current and usable.               */

@@ -43,7 +43,7 @@ class Problem(C.Structure):
 
 class Outputs(C.Structure):
     _fields_ = [
-        ("per_step", _dp), ("per_step_mask", C.c_uint32), ("reserved0", C.c_int32),
+        ("per_step", _dp), ("per_step_mask", C.c_uint32), ("tile_diag_rows", C.c_int32),
         ("sums", _dp), ("start_volume", _dp), ("status", _dp), ("crash_step", _dp),
         ("num_fronts", _dp), ("fronts", _dp), ("front_layer", _dp), ("front_to_bottom", _dp),
         ("counters", _dp), ("tile_cycles", _dp),

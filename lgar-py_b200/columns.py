@@ -165,7 +165,7 @@ class ForwardResult:
     front_layer: Optional[torch.Tensor] = None     # [T,16,B]
     front_to_bottom: Optional[torch.Tensor] = None # [T,16,B]
     counters: Optional[torch.Tensor] = None        # [16] int64: 8 work counters + phase timers (lgar_b200.h)
-    tile_cycles: Optional[torch.Tensor] = None     # [ceil(B/32)] int64 (diagnostics)
+    tile_cycles: Optional[torch.Tensor] = None     # [ceil(B/32)] int64 (diagnostics); [3, ceil(B/32)] with counters
     overflow_reruns: int = 0                       # columns rerun with the 32-front kernel (overflow_fallback)
 
     def __getitem__(self, name) -> torch.Tensor:
@@ -273,8 +273,11 @@ def forward_raw(ens: ColumnEnsemble, alpha, n, ksat, outputs=("runoff", "percola
         res.counters = torch.zeros(16, dtype=torch.int64, device=dev)
         o.counters = res.counters.data_ptr()
     if tile_cycles:
-        res.tile_cycles = torch.zeros((B + 31) // 32, dtype=torch.int64, device=dev)
+        # with the counting kernel: [3, tiles] = busy cycles, cycles waiting for the predecessor chunk, finish time (ns)
+        rows = 3 if counters else 1
+        res.tile_cycles = torch.zeros((rows, (B + 31) // 32) if rows == 3 else ((B + 31) // 32,), dtype=torch.int64, device=dev)
         o.tile_cycles = res.tile_cycles.data_ptr()
+        o.tile_diag_rows = rows
     stream = torch.cuda.current_stream(dev).cuda_stream
     with torch.cuda.device(dev):
         rc = L_.lgar_forward(C.byref(p), C.byref(o), workspace.data_ptr(), workspace.numel(),

@@ -320,7 +320,7 @@ int lgar_forward(const lgar_problem* p, const lgar_outputs* out, void* workspace
   if (p->pipeline_seq <= 1) {  // (a memset between two kernels of a pipelined sequence would serialise them)
     if (out->counters) CUDA_TRY(cudaMemsetAsync(out->counters, 0, 16 * sizeof(unsigned long long), st));
     if (out->tile_cycles)
-      CUDA_TRY(cudaMemsetAsync(out->tile_cycles, 0, (size_t)s.ntiles * sizeof(unsigned long long), st));
+      CUDA_TRY(cudaMemsetAsync(out->tile_cycles, 0, (size_t)(out->tile_diag_rows == 3 ? 3 : 1) * s.ntiles * sizeof(unsigned long long), st));
   }
   // the kernels without work counters are trapezoid-only (closed-form branch compiled out of the hot path)
   const bool count = out->counters != nullptr || p->use_closed_form_G != 0;
@@ -442,7 +442,7 @@ int lgar_forward_host(const lgar_problem* ph, const lgar_outputs* oh) {
   AL(per_step, (size_t)__builtin_popcount(oh->per_step_mask) * T * B) AL(sums, (size_t)LGAR_NUM_OUTPUTS * B) AL(start_volume, B)
   AL(status, B) AL(crash_step, B) AL(num_fronts, T * B) AL(fronts, T * LGAR_MAX_FRONTS * 5 * B)
   AL(front_layer, T * LGAR_MAX_FRONTS * B) AL(front_to_bottom, T * LGAR_MAX_FRONTS * B) AL(counters, 16)
-  AL(tile_cycles, (size_t)s.ntiles)
+  AL(tile_cycles, (size_t)(oh->tile_diag_rows == 3 ? 3 : 1) * s.ntiles)
 #undef AL
   const size_t wsb = lgar_workspace_bytes(&p, 0);
   void* ws = nullptr;
@@ -456,7 +456,7 @@ int lgar_forward_host(const lgar_problem* ph, const lgar_outputs* oh) {
   DOWN(per_step, (size_t)__builtin_popcount(oh->per_step_mask) * T * B) DOWN(sums, (size_t)LGAR_NUM_OUTPUTS * B) DOWN(start_volume, B)
   DOWN(status, B) DOWN(crash_step, B) DOWN(num_fronts, T * B) DOWN(fronts, T * LGAR_MAX_FRONTS * 5 * B)
   DOWN(front_layer, T * LGAR_MAX_FRONTS * B) DOWN(front_to_bottom, T * LGAR_MAX_FRONTS * B) DOWN(counters, 16)
-  DOWN(tile_cycles, (size_t)s.ntiles)
+  DOWN(tile_cycles, (size_t)(oh->tile_diag_rows == 3 ? 3 : 1) * s.ntiles)
 #undef DOWN
   return 0;
 }

@@ -1731,14 +1731,22 @@ struct Column {
             f(F_DEPTH, fd) = cand;
             const double m = mass_balance_t<double>();
             const double e = fabs(m - mass_timestep);
+            // (mass monotone in the depth: the iterates in between lie between the two end points.  Either the mass
+            // moves by more than the rounding noise per step, or both end points are far (> 1e-9) from the
+            // [0, 2e-12] window the loop stops in -- the FLAT case: theta of the free-drainage front equals theta of
+            // the front below, the mass does not depend on the depth, the reference never leaves the loop
+            // (Layer.py:681-701 has no stall guard) and this column ends with ITER_CAP.  Without the second clause
+            // such a column walked its million iterations one by one: 1.7 s of a warp, 2.5 % of the bench shard's
+            // work and, when it happened in the last rows of the record, the tail of the whole pass.)
             const bool cont = (up ? (m < mass_timestep) : !(m < mass_timestep)) && (fabs(e - 1e-12) > 1e-12) &&
                               (fabs(cand) >= 64.0 * step) && ((cand < 0.0) == (depth_new < 0.0)) &&
-                              fabs(m - current_mass) >= 1e-13 * (double)stride;
+                              (fabs(m - current_mass) >= 1e-13 * (double)stride || (e > 1e-9 && err > 1e-9));
             if (cont) {  // identical to `stride` regular iterations of this run
               depth_new = cand;
               current_mass = m;
               err = e;
               it += stride;
+              if (it > c.iter_cap) break;  // (a flat run never ends: the outer loop raises ITER_CAP)
               stride = shrinking ? (stride >> 1) : (stride << 1);
               if (stride > (1LL << 40)) stride = 1LL << 40;
             } else {

@@ -658,10 +658,13 @@ __global__ void __launch_bounds__(NT, (FM == 32) ? 1 : ((FM == 16) ? 2 : ((FM ==
     // wait for the previous chunk of this tile (acquire): done[tile] = forcing rows completed (absolute row index)
     const int t0 = K.t_begin + chunk * K.chunk_steps;
     const int t1 = min(K.t_end, t0 + K.chunk_steps);
+    long long wait_cyc = 0;  // (counting kernel: scheduler diagnostics, lgar_outputs.tile_diag_rows)
     if (chunk > 0 || K.overlap) {
       if (lane == 0) {
+        const long long w0 = COUNT ? clock64() : 0;
         volatile int32_t* d = K.done + tile;
         while (*d < t0) __nanosleep(200);
+        if (COUNT) wait_cyc = clock64() - w0;
       }
       __syncwarp();
       __threadfence();
@@ -781,6 +784,12 @@ __global__ void __launch_bounds__(NT, (FM == 32) ? 1 : ((FM == 16) ? 2 : ((FM ==
     __syncwarp();
     if (lane == 0) {
       if (K.o.tile_cycles) atomicAdd(K.o.tile_cycles + tile, (unsigned long long)(clock64() - clk0));
+      if (COUNT && K.o.tile_cycles && K.o.tile_diag_rows == 3) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        atomicAdd(K.o.tile_cycles + K.ntiles + tile, (unsigned long long)wait_cyc);
+        atomicMax(K.o.tile_cycles + 2 * (size_t)K.ntiles + tile, now);
+      }
       atomicExch(K.done + tile, t1);
     }
   }

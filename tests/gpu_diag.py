@@ -7,7 +7,8 @@ import lgar_b200
 from lgar_b200 import workloads, ColumnEnsemble, forward_raw
 shapes = [tuple(int(x) for x in a.split("x")) for a in sys.argv[1:]] or [(2048, 256)]
 for B, T in shapes:
-    we = workloads.synthetic_sites_ensemble(B=B, T=T, sites=max(1, min(128, B // 32)), rank=int(os.environ.get("LGAR_DIAG_RANK", "0")))
+    we = workloads.synthetic_sites_ensemble(B=B, T=T, sites=max(1, min(128, B // 32)), rank=int(os.environ.get("LGAR_DIAG_RANK", "0")),
+                                             shared_sites=bool(os.environ.get("LGAR_DIAG_SHARED")))
     sl = os.environ.get("LGAR_DIAG_SLICE")
     if sl:
         a, cnt = (int(x) for x in sl.split(":"))
@@ -46,7 +47,18 @@ for B, T in shapes:
     if os.environ.get("LGAR_DIAG_SAVE"):
         os.makedirs("gpurun_out", exist_ok=True)
         np.savez_compressed(f"gpurun_out/diag_{B}x{T}{os.environ.get('LGAR_DIAG_TAG', '')}.npz", sums=res.sums.cpu().numpy(), status=st, crash=cr)
-    tc = res.tile_cycles.cpu().numpy(); top = np.argsort(-tc)[:4]
+    tc = res.tile_cycles.cpu().numpy()
+    if tc.ndim == 2:  # counting kernel: busy cycles, wait cycles, finish time (ns) per tile
+        wait, fin = tc[1].astype(np.float64), tc[2].astype(np.float64)
+        tc = tc[0]
+        rel = (fin.max() - fin) * 1e-9
+        wtop = np.argsort(-wait)[:4]
+        print(f"  scheduler: warps blocked on a predecessor chunk {wait.sum() / 1.965e9:.1f} warp-s = {wait.sum() / 1.965e9 / 1184:.3f} s per resident warp; "
+              f"most waited-for tiles {[(int(i), round(float(wait[i]) / 1.965e9, 2)) for i in wtop]}", flush=True)
+        print(f"  tail: last tile finishes {np.percentile(rel, 50):.3f} s after the median tile, {np.percentile(rel, 10):.3f} s after the 90th percentile, "
+              f"{np.sort(rel)[min(len(rel) - 1, 1184)]:.3f} s after all but 1184 tiles, {np.sort(rel)[min(len(rel) - 1, 148)]:.3f} s after all but 148; "
+              f"last tiles {[(int(i), round(float(rel[i]), 3)) for i in np.argsort(rel)[:6]]}", flush=True)
+    top = np.argsort(-tc)[:4]
     print(f"  tile busy time: sum {tc.sum() / 1.965e9:.1f} s = {tc.sum() / 1.965e9 / 1184:.3f} s per resident warp (1184), "
           f"max {tc.max() / 1.965e9:.3f} s, mean {tc.mean() / 1.965e9:.4f} s, p99 {np.percentile(tc, 99) / 1.965e9:.3f} s", flush=True)
     if os.environ.get("LGAR_DIAG_TILES"):
