@@ -159,3 +159,33 @@ def test_front_overflow_fallback():
     ok = ref.status == 0
     assert torch.equal(fb.sums[:, ok].contiguous().view(torch.int64), ref.sums[:, ok].contiguous().view(torch.int64))
     assert torch.equal(fb["runoff"][:, ok].contiguous().view(torch.int64), ref["runoff"][:, ok].contiguous().view(torch.int64))
+
+
+def test_flat_column_mass_run_ends_with_iter_cap_quickly():
+    """A column whose free-drainage front has the theta of the front below it: the column mass does not depend on the
+    depth check_column_mass steps (Layer.py:681-701), the reference never leaves that loop, this library answers with
+    the capacity status ITER_CAP -- at the step where the oracle's literal loop passes 1e6 iterations, and WITHOUT
+    walking the million iterations (it was 1.7 s of a warp and the tail of the whole bench pass: DESIGN.md 4.1/5).
+    Column 84815 of shard 4 of the C4 bench ensemble, found with tests/gpu_diag_tile.py."""
+    from lgar_b200 import workloads, forward_raw, STATUS_NAMES
+    from oracle import lgar_oracle as O
+    T, b = 8760, 84815
+    we = workloads.synthetic_sites_ensemble(B=125_000, T=T, sites=128, rank=4, shared_sites=True)
+    cols = np.array([b] * 32)
+    ens = _ens(we, cols)
+    a, n, k = (np.ascontiguousarray(x[:, cols]) for x in (we.alpha, we.n, we.ksat))
+    res, ws = forward_raw(ens, a, n, k, outputs=(), per_step=False, window=(0, 8640), counters=True)
+    torch.cuda.synchronize()
+    before = res.counters.cpu().numpy().astype(np.int64)
+    assert (res.status.cpu().numpy() == 0).all()
+    res, ws = forward_raw(ens, a, n, k, outputs=(), per_step=False, workspace=ws, window=(8640, T), into=res, counters=True)
+    torch.cuda.synchronize()
+    st, cr = res.status.cpu().numpy(), res.crash_step.cpu().numpy()
+    cfg = O.make_cfg(we.alpha[:, b], we.n[:, b], we.ksat[:, b], we.theta_r[:, b], we.theta_e[:, b], thickness=we.thickness[:, b],
+                     iter_cap=1_000_000)
+    r = O.forward(cfg, we.forcing[we.site_index[b]], fronts=False)
+    assert STATUS_NAMES[int(r["status"])] == "ITER_CAP"
+    assert (st == r["status"]).all() and (cr == r["crash_step"]).all(), (st[:2], cr[:2], r["status"], r["crash_step"])
+    colmass = int(res.counters.cpu().numpy()[6])  # check_column_mass evaluations of the last 120 rows, 32 lanes
+    assert colmass < 32 * 20_000, f"{colmass} column-mass evaluations: the flat run was walked, not jumped"
+    del before
