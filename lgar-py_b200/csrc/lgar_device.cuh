@@ -1445,7 +1445,118 @@ __device__ __forceinline__ Var geffq_get(GeffQueue* q, int slot, const Var& t1, 
   const double d[5] = {dq[0 * 32], dq[1 * 32], dq[2 * 32], dq[3 * 32], dq[4 * 32]};
   return tape_record_n(q->a[slot], 5, ids, d);
 }
-__device__ __forceinline__ void geffq_eval(GeffQueue* q, const SoilT<double>* soil, int L, int nint, bool split = false) {
+// ------------------------------------------------------------------------------------
+// Dealt batches: P = 2, 4 or 8 LANES PER REQUEST for the last, partly filled batch of a phase (forward values only).
+// A batch costs the latency of one whole request (60 passes of the pair evaluator) however many of its 32 slots are
+// filled, and the bench ensemble fills 77 % of them (the requests of a warp-step, ~50, rarely come in multiples of 32).
+// When at most 32 / P requests are left they are dealt over all lanes instead: the nodes of a request go round-robin,
+// in pairs, to the P lanes of its group (lane `sub` takes the pairs sub, sub + P, ...), so a batch takes
+// ceil(nint / 2P) passes.  Bits are those of the literal loop: every lane walks the SAME chain of rounded additions
+// `h = h + dh` (and skips the nodes that are not its own: 2 (P - 1) additions per pass), and the running sum
+// `geff = geff + (k1 + k2) * (dh / 2)` travels through the P lanes in node order once per pass (two shuffles per
+// hand-over) -- nothing is buffered and the node evaluation is the one out-of-line pair evaluator of everything else.
+// The guards keep the reference's order: the first node (in node order) that raises wins.
+// MEASURED SLOWER and therefore compiled out by default (-DLGAR_GEFF_DEAL=1 enables it): bit-identical results (all 101
+// GPU tests green, incl. the bit-exact full-year columns), but the full-year forward pass of the C4 shard took 19.61 s
+// against 19.27 s (48.4 M against 49.3 M column-steps/s, profiles/bench_r2c_ab_deal.json).  Like the eight-lanes-per-
+// request split above: a partly filled batch is cheaper than its pass count suggests (the pair evaluator's FP64
+// instructions of the other resident warps fill the pipe while this warp waits), and the hand-over + redundant end
+// points are not free.  Kept as the A/B that closes the "fill the remainder batch" question.
+// ------------------------------------------------------------------------------------
+#ifndef LGAR_GEFF_DEAL
+#define LGAR_GEFF_DEAL 0
+#endif
+template <class ST>
+__device__ __noinline__ void geff_batch_eval_deal(GeffQueue* q, const ST* soil, int L, int nint, int P) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (P - 1), base = lane - sub;
+  const int slot = lane / P;
+  const int meta = q->meta[slot];
+  const bool have = meta >= 0;
+  const Soil s = gather_soil(soil, L, have ? (meta & 31) : lane, have ? ((meta >> 8) & 7) : 0);
+  double h_i = 0.0, dh = 0.0, k_last = 0.0;
+  int st_a = 0;
+  if (have) {  // end points, redundantly in the P lanes of the group (same operands, same bits)
+    Ctx c;
+    c.st = 0;
+    const double se_i = se_from_theta(q->a[slot], s, c);
+    const double se_f = se_from_theta(q->b[slot], s, c);
+    const double2 hh = h_from_se_x2(se_i, se_f, s, c);
+    h_i = hh.x;
+    const double h_f = hh.y;
+    if (fabs(h_i) >= 0.1 && s.alpha * h_i < 0.0) raise(c, LGAR_ST_NEG_POW);
+    if (fabs(h_f) >= 0.1 && s.alpha * h_f < 0.0) raise(c, LGAR_ST_NEG_POW);
+    dh = (h_f - h_i) / (double)nint;
+    k_last = k_from_se(se_i, s.ksat, s.m, s.inv_m, c);
+    st_a = c.st;
+  }
+  __syncwarp();  // every lane has read its request before any result is written back into the queue
+  const double half = dh / 2.0;
+  double h2 = h_i + dh;                                 // node 1 ...
+  for (int w = 0; w < 2 * sub; w++) h2 = h2 + dh;       // ... node 2 sub + 1: this lane's first node
+  double geff = 0.0;
+  int bad_st = 0, bad_key = 0x7fffffff;                 // first raising node of this lane: status, (pass, sub)
+  const int npass = (nint + 2 * P - 1) / (2 * P);
+#pragma unroll 1
+  for (int pass = 0; pass < npass; pass++) {            // (warp-uniform)
+    const int n0 = (pass * P + sub) * 2 + 1;            // this lane's nodes: n0, n0 + 1
+    const bool va = have && n0 <= nint, vb = have && n0 + 1 <= nint;
+    double2 kk = make_double2(0.0, 0.0);
+    if (va) {
+      const double ha = h2, hb = ha + dh;
+      int bad;
+      kk = k_nodes_core_x2(ha, vb ? hb : ha, s.alpha, s.n, s.m, s.inv_m, s.ksat, &bad);
+      h2 = hb + dh;
+      for (int w = 0; w < 2 * (P - 1); w++) h2 = h2 + dh;
+      if (bad_st == 0) {
+        const int b = bad ? bad : ((isnan(kk.x) || (vb && isnan(kk.y))) ? LGAR_ST_NAN : 0);
+        if (b) {
+          bad_st = b;
+          bad_key = pass * P + sub;
+        }
+      }
+    }
+    // the running sum and the K of the node before go through the group in node order
+#pragma unroll 1
+    for (int qd = 0; qd < P; qd++) {
+      const int src = base + ((qd + P - 1) & (P - 1));
+      const double g_in = shfl_d(geff, src), k_in = shfl_d(k_last, src);
+      if (sub == qd) {
+        double g = geff, k1 = k_last;
+        if (pass > 0 || qd > 0) {
+          g = g_in;
+          k1 = k_in;
+        }
+        if (va) {
+          g = g + ((k1 + kk.x) * half);
+          k1 = kk.x;
+        }
+        if (vb) {
+          g = g + ((k1 + kk.y) * half);
+          k1 = kk.y;
+        }
+        geff = g;
+        k_last = k1;
+      }
+    }
+  }
+  const double g_fin = shfl_d(geff, base + P - 1);      // the lane that closed the last pass holds the sum
+  for (int d = 1; d < P; d <<= 1) {                     // earliest raising node of the group
+    const int ok = __shfl_xor_sync(FULL, bad_key, d), os = __shfl_xor_sync(FULL, bad_st, d);
+    if (ok < bad_key) {
+      bad_key = ok;
+      bad_st = os;
+    }
+  }
+  if (have && sub == 0) {
+    q->a[slot] = fabs(g_fin / s.ksat);
+    q->st[slot] = st_a ? st_a : bad_st;
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void geffq_eval(GeffQueue* q, const SoilT<double>* soil, int L, int nint, bool split = false, int deal = 1) {
 #if LGAR_GEFF_SPLIT_UP_TO > 0
   if (split) {
     geff_batch_eval_split(q, soil, L, nint);
@@ -1453,9 +1564,13 @@ __device__ __forceinline__ void geffq_eval(GeffQueue* q, const SoilT<double>* so
   }
 #endif
   (void)split;
+  if (LGAR_GEFF_DEAL && deal > 1) {
+    geff_batch_eval_deal(q, soil, L, nint, deal);
+    return;
+  }
   geff_batch_eval(q, soil, L, nint);
 }
-__device__ __forceinline__ void geffq_eval(GeffQueue* q, const SoilT<Var>* soil, int L, int nint, bool split = false) {
+__device__ __forceinline__ void geffq_eval(GeffQueue* q, const SoilT<Var>* soil, int L, int nint, bool split = false, int /*deal*/ = 1) {
 #if LGAR_GEFF_SPLIT_UP_TO > 0
   if (split) {
     geff_batch_eval_split_taped(q, soil, L, nint);

@@ -344,7 +344,13 @@ __device__ void substep(Tile<FM, R, LM>& T, bool act, double precip_rate, double
     int rem = nreq;
     for (int lo = 0; lo < total;) {
       const bool split = (total - lo) <= GEFF_SPLIT_UP_TO;  // warp-uniform
-      const int hi = lo + (split ? GEFF_SPLIT_SLOTS : 32);
+      // the last, partly filled batch of the phase is dealt over all lanes (forward values only: geff_batch_eval_deal)
+      int deal = 1;
+      if (LGAR_GEFF_DEAL && !Column<FM, R, LM>::TAPED && !split) {
+        const int left = total - lo;
+        deal = (left <= 4) ? 8 : ((left <= 8) ? 4 : ((left <= 16) ? 2 : 1));
+      }
+      const int hi = lo + (split ? GEFF_SPLIT_SLOTS : (32 / deal));
       gq->meta[lane] = -1;
       __syncwarp();
       {
@@ -359,7 +365,7 @@ __device__ void substep(Tile<FM, R, LM>& T, bool act, double precip_rate, double
         }
       }
       __syncwarp();
-      geffq_eval(gq, C.soil, K.p.num_layers, nint, split);
+      geffq_eval(gq, C.soil, K.p.num_layers, nint, split, deal);
       while (rem > 0 && g < hi) {
         const int i = cur++;
         if (C.tb(i)) continue;
