@@ -1847,15 +1847,17 @@ struct Column {
             const double m = mass_balance_t<double>();
             const double e = fabs(m - mass_timestep);
             // (mass monotone in the depth: the iterates in between lie between the two end points.  Either the mass
-            // moves by more than the rounding noise per step, or both end points are far (> 1e-9) from the
-            // [0, 2e-12] window the loop stops in -- the FLAT case: theta of the free-drainage front equals theta of
+            // moves by more than the rounding noise per step, or both end points are far (> 1e-11, a hundred times the
+            // rounding noise of a column mass) from the [0, 2e-12] window the loop stops in, or the step has fallen
+            // below the spacing of the depth (cand == depth_new: nothing can change any more) -- the FLAT case: theta
+            // of the free-drainage front equals theta of
             // the front below, the mass does not depend on the depth, the reference never leaves the loop
             // (Layer.py:681-701 has no stall guard) and this column ends with ITER_CAP.  Without the second clause
             // such a column walked its million iterations one by one: 1.7 s of a warp, 2.5 % of the bench shard's
             // work and, when it happened in the last rows of the record, the tail of the whole pass.)
             const bool cont = (up ? (m < mass_timestep) : !(m < mass_timestep)) && (fabs(e - 1e-12) > 1e-12) &&
                               (fabs(cand) >= 64.0 * step) && ((cand < 0.0) == (depth_new < 0.0)) &&
-                              (fabs(m - current_mass) >= 1e-13 * (double)stride || (e > 1e-9 && err > 1e-9));
+                              (fabs(m - current_mass) >= 1e-13 * (double)stride || (e > 1e-11 && err > 1e-11) || cand == depth_new);
             if (cont) {  // identical to `stride` regular iterations of this run
               depth_new = cand;
               current_mass = m;
